@@ -1,0 +1,581 @@
+// Chain-batched, *iterative* NUTS / HamiltonianMC state machine.
+//
+// One "group" of threads (a warp, or a whole block for large D) owns one chain.  The chain
+// is a small state machine whose unit of progress is ONE leapfrog: `b2_advance()` consumes
+// the (logp, grad) that was just evaluated at the chain's pending position, performs all the
+// tree bookkeeping that follows from it (second half-kick, energy, divergence test, sub-tree
+// merges with U-turn checks and multinomial picks, the top-level merge, end-of-transition
+// adaptation and trace write, the next transition's momentum draw ...) and leaves behind the
+// next position to evaluate.  Lock-step kernels alternate {gradient kernel, advance kernel};
+// the persistent kernel loops {model gradient, advance} inside one launch.
+//
+// Reference behaviour restated here (no recursion, no Python objects):
+//   pymc3/step_methods/hmc/nuts.py:168-188   NUTS._hamiltonian_step (depth loop, early depth 8)
+//   pymc3/step_methods/hmc/nuts.py:254-309   _Tree.extend        -> top_merge()
+//   pymc3/step_methods/hmc/nuts.py:311-345   _Tree._single_step  -> finish_leaf()
+//   pymc3/step_methods/hmc/nuts.py:347-389   _Tree._build_subtree-> binary-counter merges
+//   pymc3/step_methods/hmc/nuts.py:391-406   _Tree.stats
+//   pymc3/step_methods/hmc/integration.py:81-109  leapfrog
+//   pymc3/step_methods/hmc/hmc.py:110-152    HamiltonianMC._hamiltonian_step
+//   pymc3/step_methods/hmc/base_hmc.py:133-199  BaseHMC.astep
+//   pymc3/step_methods/step_sizes.py:21-58   DualAverageAdaptation
+//   pymc3/step_methods/hmc/quadpotential.py:140-225, 313-353  QuadPotentialDiagAdapt
+//
+// The header is host/device neutral: tests/hostsim builds it with a one-thread "group" so the
+// exact same logic is checked against the CPU oracle without a GPU.  The product never runs
+// that build (the shipped library contains device kernels only).
+#pragma once
+#include "b2_philox.cuh"
+
+#define B2_MAX_LEVELS 12          // stack buffers; max_treedepth <= 12
+
+enum { B2_PHASE_INIT = 0, B2_PHASE_TREE = 1, B2_PHASE_HMC = 2, B2_PHASE_DONE = 3, B2_PHASE_FAILED = 4 };
+enum { B2_KIND_NUTS = 0, B2_KIND_HMC = 1 };
+enum { B2_FAIL_NONE = 0, B2_FAIL_BAD_INITIAL_ENERGY = 1 };
+
+// vector slots in the per-engine state buffer, each [n_chains][Dp]
+enum {
+    B2_V_QE0 = 0, B2_V_QE1, B2_V_PE0, B2_V_PE1, B2_V_GE0, B2_V_GE1,   // left / right edge (q, p, grad)
+    B2_V_POLD, B2_V_PSUM, B2_V_PROPQ, B2_V_PROPG, B2_V_VAR,
+    B2_V_STACK0,                                                       // then 5 per stack buffer
+};
+enum { B2_S_PFIRST = 0, B2_S_PLAST, B2_S_PSUM, B2_S_Q, B2_S_G, B2_S_NVEC };
+#define B2_NUM_VEC_SLOTS (B2_V_STACK0 + B2_S_NVEC * B2_MAX_LEVELS)
+
+struct B2ChainState {
+    int phase, iter, fail_code, sel;            // sel: which edge holds the pending position
+    uint32_t key0, key1;
+    // dual averaging (step_sizes.py)
+    double log_step, log_bar, hbar, mu;
+    int da_count;
+    // QuadPotentialDiagAdapt bookkeeping
+    int n_seen, window, fg_sel;
+    double wv_count[2];
+    // current point
+    double cur_logp;
+    // transition in flight
+    double eps, step_used, e0;
+    int depth, max_depth, dir, leaf_n;
+    double log_size, log_accept, max_de, prop_energy, prop_logp;
+    int n_prop, diverged, turned;
+    unsigned long long slot_map;
+    double lv_log_size[B2_MAX_LEVELS], lv_log_accept[B2_MAX_LEVELS];
+    double lv_energy[B2_MAX_LEVELS], lv_logp[B2_MAX_LEVELS];
+    // HMC
+    int hmc_n_steps, hmc_step;
+    // run counters
+    int n_div_post, n_maxdepth_post, n_post;
+    long long n_grad;
+};
+
+template <typename T>
+struct B2View {
+    // geometry
+    int C, D, Dp;
+    // state
+    T* vec;                       // [B2_NUM_VEC_SLOTS][C][Dp]
+    double* wv_mean;              // [2][C][Dp]  Welford means   (always fp64, quadpotential.py:321-327)
+    double* wv_m2;                // [2][C][Dp]  Welford raw variances
+    B2ChainState* st;             // [C]
+    double* logp_eval;            // [C]  written by the gradient kernel (lock-step mode)
+    // sampler options
+    int kind;                     // NUTS | HMC
+    int iter_base, iter_end, tune_until;
+    int max_treedepth, early_max_treedepth;
+    double emax, target, gamma, k, t0;
+    int adapt_step, adapt_mass;
+    double path_length;
+    int max_steps, hmc_jitter;
+    // trace outputs (row = iter - iter_base), any may be null
+    T* tr_q;                      // [n][C][D]
+    double *tr_energy, *tr_energy_error, *tr_max_energy_error, *tr_mean_tree_accept;
+    double *tr_step_size, *tr_step_size_bar, *tr_model_logp, *tr_accept;
+    int *tr_depth, *tr_tree_size, *tr_n_steps;
+    unsigned char *tr_diverging, *tr_tune, *tr_accepted;
+
+    B2_HD T* V(int slot, int c) const { return vec + ((size_t)slot * C + c) * Dp; }
+    B2_HD T* S(int buf, int which, int c) const { return V(B2_V_STACK0 + buf * B2_S_NVEC + which, c); }
+};
+
+// ----------------------------------------------------------------------------- thread groups
+struct B2HostGroup {                       // tests only: one "lane"
+    static constexpr int NT = 1;
+    B2_HD int lane() const { return 0; }
+    template <int K> B2_HD void allsum(double (&x)[K]) const {}
+    B2_HD void sync() const {}
+};
+
+#if defined(__CUDACC__)
+struct B2WarpGroup {                       // warp per chain
+    static constexpr int NT = 32;
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    template <int K> __device__ __forceinline__ void allsum(double (&x)[K]) const {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
+        }
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+template <int NTHREADS>
+struct B2BlockGroup {                      // block per chain (large D)
+    static constexpr int NT = NTHREADS;
+    double* red;                           // shared scratch, >= 8 * (NT/32) doubles
+    __device__ __forceinline__ int lane() const { return threadIdx.x; }
+    template <int K> __device__ __forceinline__ void allsum(double (&x)[K]) const {
+        static_assert(K <= 8, "scratch sized for 8 simultaneous sums");
+        constexpr int NW = NT / 32;
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
+        }
+        __syncthreads();                   // previous users of `red` are done
+        if (l == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) red[k * NW + w] = x[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int j = 0; j < NW; ++j) s += red[k * NW + j];   // same order in every thread
+            x[k] = s;
+        }
+    }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+#endif
+
+// ----------------------------------------------------------------------------- small math
+B2_HD double b2_logaddexp(double a, double b) {          // numpy.logaddexp semantics
+    if (a == b) return a + 0.693147180559945309417232121458;
+    double d = a - b;
+    if (d > 0) return a + log1p(exp(-d));
+    if (d <= 0) return b + log1p(exp(d));
+    return a + b;                                        // NaN
+}
+B2_HD bool b2_finite(double x) { return (x - x) == 0.0; }
+
+B2_HD int b2_map_get(unsigned long long m, int level) { return (int)((m >> (4 * level)) & 0xFull); }
+B2_HD unsigned long long b2_map_swap(unsigned long long m, int a, int b) {
+    unsigned long long va = (m >> (4 * a)) & 0xFull, vb = (m >> (4 * b)) & 0xFull;
+    m &= ~((0xFull << (4 * a)) | (0xFull << (4 * b)));
+    return m | (vb << (4 * a)) | (va << (4 * b));
+}
+#define B2_MAP_IDENTITY 0xBA9876543210ull
+
+// U-turn tests of nuts.py:361-370 / :298-307 for two adjacent sub-trajectories t1 | t2
+// (t1 built earlier / on the left).  v = var (.) p  (quadpotential.py:185-187).
+// Optionally writes the merged p_sum to `out_psum` and t2's last momentum to `out_plast`.
+template <typename T, typename G>
+B2_HD bool b2_uturn(const G& g, int D, const T* var,
+                    const T* first1, const T* last1, const T* psum1,
+                    const T* first2, const T* last2, const T* psum2,
+                    bool extra, T* out_psum, T* out_plast) {
+    double d[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = g.lane(); i < D; i += G::NT) {
+        const T vr = var[i];
+        const T f1 = first1[i], l1 = last1[i], s1 = psum1[i];
+        const T f2 = first2[i], l2 = last2[i], s2 = psum2[i];
+        const T tot = s1 + s2;
+        d[0] += (double)(tot * (vr * f1));
+        d[1] += (double)(tot * (vr * l2));
+        if (extra) {
+            const T a = s1 + f2;
+            d[2] += (double)(a * (vr * f1));
+            d[3] += (double)(a * (vr * f2));
+            const T b = l1 + s2;
+            d[4] += (double)(b * (vr * l1));
+            d[5] += (double)(b * (vr * l2));
+        }
+        if (out_psum) out_psum[i] = tot;
+        if (out_plast) out_plast[i] = l2;
+    }
+    g.allsum(d);
+    bool turning = (d[0] <= 0) || (d[1] <= 0);
+    if (extra) turning = turning || (d[2] <= 0) || (d[3] <= 0) || (d[4] <= 0) || (d[5] <= 0);
+    return turning;
+}
+
+template <typename T, typename G>
+B2_HD void b2_copy(const G& g, int D, T* dst, const T* src) {
+    for (int i = g.lane(); i < D; i += G::NT) dst[i] = src[i];
+}
+
+// first half-kick + drift, in place on edge `e`:  integration.py:90-99
+template <typename T, typename G>
+B2_HD void b2_prepare_leapfrog(const G& g, const B2View<T>& w, int c, int e, double eps_signed) {
+    T* q = w.V(B2_V_QE0 + e, c);
+    T* p = w.V(B2_V_PE0 + e, c);
+    const T* gr = w.V(B2_V_GE0 + e, c);
+    const T* var = w.V(B2_V_VAR, c);
+    const T eps = (T)eps_signed, half = (T)(0.5 * eps_signed);
+    for (int i = g.lane(); i < w.D; i += G::NT) {
+        const T pm = p[i] + half * gr[i];
+        p[i] = pm;
+        q[i] = q[i] + eps * (var[i] * pm);
+    }
+}
+
+// second half-kick and energy:  integration.py:101-107
+template <typename T, typename G>
+B2_HD double b2_finish_leapfrog(const G& g, const B2View<T>& w, int c, int e, double eps_signed, double logp) {
+    T* p = w.V(B2_V_PE0 + e, c);
+    const T* gr = w.V(B2_V_GE0 + e, c);
+    const T* var = w.V(B2_V_VAR, c);
+    const T half = (T)(0.5 * eps_signed);
+    double kin[1] = {0.0};
+    for (int i = g.lane(); i < w.D; i += G::NT) {
+        const T pn = p[i] + half * gr[i];
+        p[i] = pn;
+        kin[0] += (double)(pn * (var[i] * pn));
+    }
+    g.allsum(kin);
+    return 0.5 * kin[0] - logp;
+}
+
+// ------------------------------------------------------------------------ chain initialisation
+// Mirrors what the reference sets up per chain before the first draw:
+//   base_hmc.py:93-96  (initial step size -> DualAverageAdaptation, step_sizes.py:22-32)
+//   quadpotential.py:140-183 (QuadPotentialDiagAdapt: foreground window seeded with
+//   `initial_weight` pseudo-samples of (mean, var); empty background window)
+//   sampling.py:883-884 (per-chain seed) -> Philox key.
+template <typename T, typename G>
+B2_HD void b2_init_chain(const G& g, const B2View<T>& w, int c, B2ChainState& s, const T* q0,
+                         unsigned long long seed, double step0, const double* mass_mean,
+                         const double* mass_var, double mass_weight, int window, int iter0) {
+    s.phase = B2_PHASE_INIT; s.iter = iter0; s.fail_code = B2_FAIL_NONE; s.sel = 1;
+    s.key0 = (uint32_t)(seed & 0xFFFFFFFFull); s.key1 = (uint32_t)(seed >> 32);
+    s.log_step = log(step0); s.log_bar = s.log_step; s.hbar = 0.0; s.mu = log(10.0 * step0); s.da_count = 1;
+    s.n_seen = 0; s.window = window; s.fg_sel = 0; s.wv_count[0] = mass_weight; s.wv_count[1] = 0.0;
+    s.cur_logp = 0.0; s.eps = step0; s.step_used = step0; s.e0 = 0.0;
+    s.depth = 0; s.max_depth = 0; s.dir = 1; s.leaf_n = 0;
+    s.log_size = 0.0; s.log_accept = 0.0; s.max_de = 0.0; s.prop_energy = 0.0; s.prop_logp = 0.0;
+    s.n_prop = 0; s.diverged = 0; s.turned = 0; s.slot_map = B2_MAP_IDENTITY;
+    for (int l = 0; l < B2_MAX_LEVELS; ++l) { s.lv_log_size[l] = 0; s.lv_log_accept[l] = 0; s.lv_energy[l] = 0; s.lv_logp[l] = 0; }
+    s.hmc_n_steps = 0; s.hmc_step = 0;
+    s.n_div_post = 0; s.n_maxdepth_post = 0; s.n_post = 0; s.n_grad = 0;
+    T *pq = w.V(B2_V_PROPQ, c), *q1 = w.V(B2_V_QE1, c), *var = w.V(B2_V_VAR, c);
+    for (int i = g.lane(); i < w.D; i += G::NT) {
+        pq[i] = q0[i]; q1[i] = q0[i];
+        var[i] = (T)mass_var[i];
+        const size_t o0 = ((size_t)0 * w.C + c) * w.Dp + i, o1 = ((size_t)1 * w.C + c) * w.Dp + i;
+        w.wv_mean[o0] = mass_mean[i]; w.wv_m2[o0] = mass_var[i] * mass_weight;
+        w.wv_mean[o1] = 0.0; w.wv_m2[o1] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------- transition start / end
+// The pieces below return an "action" so that b2_advance() can sequence them with exactly one
+// call site each (keeps the inlined device code small and the control flow group-uniform).
+enum { B2_ACT_NONE = 0, B2_ACT_TOP_MERGE, B2_ACT_END_NUTS, B2_ACT_END_NUTS_MAXDEPTH, B2_ACT_END,
+       B2_ACT_BEGIN_TRANSITION, B2_ACT_BEGIN_DOUBLING };
+
+struct B2EndStats { double accept_stat, energy, energy_error, model_logp; bool accepted; };
+
+template <typename T, typename G>
+B2_HD void b2_begin_doubling(const G& g, const B2View<T>& w, int c, B2ChainState& s) {
+    const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_DIRECTION, (uint32_t)s.depth, 0u);
+    s.dir = (log(u) < -0.693147180559945309417232121458) ? 1 : 0;        // nuts.py:177
+    b2_copy(g, w.D, w.V(B2_V_POLD, c), w.V(B2_V_PE0 + s.dir, c));
+    s.leaf_n = 0;
+    s.slot_map = B2_MAP_IDENTITY;
+    b2_prepare_leapfrog(g, w, c, s.dir, s.dir ? s.eps : -s.eps);
+    s.sel = s.dir;
+    s.phase = B2_PHASE_TREE;
+}
+
+template <typename T, typename G>
+B2_HD int b2_begin_transition(const G& g, const B2View<T>& w, int c, B2ChainState& s) {
+    const uint32_t t = (uint32_t)s.iter;
+    const bool tune = s.iter < w.tune_until;
+    const T* var = w.V(B2_V_VAR, c);
+    const T* pq = w.V(B2_V_PROPQ, c);
+    const T* pg = w.V(B2_V_PROPG, c);
+    T *q0 = w.V(B2_V_QE0, c), *q1 = w.V(B2_V_QE1, c), *p0 = w.V(B2_V_PE0, c), *p1 = w.V(B2_V_PE1, c);
+    T *g0 = w.V(B2_V_GE0, c), *g1 = w.V(B2_V_GE1, c), *ps = w.V(B2_V_PSUM, c);
+    const bool nuts = (w.kind == B2_KIND_NUTS);
+    double kin[1] = {0.0};
+    for (int i = g.lane(); i < w.D; i += G::NT) {
+        // quadpotential.py:200-203: inv_stds * normal,  inv_stds = 1 / sqrt(var)
+        const T inv_std = (T)1 / (T)sqrt((double)var[i]);
+        const T p = inv_std * (T)b2_normal(s.key0, s.key1, t, (uint32_t)i);
+        const T qq = pq[i], gg = pg[i];
+        q1[i] = qq; p1[i] = p; g1[i] = gg;
+        if (nuts) { q0[i] = qq; p0[i] = p; g0[i] = gg; ps[i] = p; }
+        kin[0] += (double)(p * (var[i] * p));
+    }
+    g.allsum(kin);
+    s.e0 = 0.5 * kin[0] - s.cur_logp;                     // integration.py:45-46
+    if (!b2_finite(s.e0)) {                               // base_hmc.py:138-158
+        s.phase = B2_PHASE_FAILED;
+        s.fail_code = B2_FAIL_BAD_INITIAL_ENERGY;
+        return B2_ACT_NONE;
+    }
+    const bool adapt = tune && w.adapt_step;
+    s.step_used = adapt ? exp(s.log_step) : exp(s.log_bar);   // step_sizes.py:34-38
+    s.eps = s.step_used;
+    s.diverged = 0; s.turned = 0;
+    if (nuts) {
+        s.depth = 0; s.log_size = 0.0; s.log_accept = -INFINITY; s.n_prop = 0; s.max_de = 0.0;
+        s.prop_energy = s.e0; s.prop_logp = s.cur_logp;
+        s.max_depth = (tune && s.iter < 200) ? w.early_max_treedepth : w.max_treedepth;   // nuts.py:169-172
+        return B2_ACT_BEGIN_DOUBLING;
+    }
+    if (w.hmc_jitter)                                     // hmc.py:26-27 via base_hmc.py:164-165
+        s.eps = (0.85 + 0.30 * b2_uniform(s.key0, s.key1, t, B2_PURPOSE_HMC_JITTER, 0u, 0u)) * s.step_used;
+    int n = (int)(w.path_length / s.eps);                 // hmc.py:111-112
+    n = n < 1 ? 1 : n;
+    s.hmc_n_steps = n > w.max_steps ? w.max_steps : n;
+    s.hmc_step = 0;
+    b2_prepare_leapfrog(g, w, c, 1, s.eps);
+    s.sel = 1;
+    s.phase = B2_PHASE_HMC;
+    return B2_ACT_NONE;
+}
+
+// base_hmc.py:169-199 tail + sampling.py:921-930 record
+template <typename T, typename G>
+B2_HD int b2_end_transition(const G& g, const B2View<T>& w, int c, B2ChainState& s, const B2EndStats& es) {
+    const bool tune = s.iter < w.tune_until;
+    const bool adapt = tune && w.adapt_step;
+    if (adapt) {                                          // step_sizes.py:40-52
+        const double cnt = (double)s.da_count;
+        const double ww = 1.0 / (cnt + w.t0);
+        s.hbar = (1.0 - ww) * s.hbar + ww * (w.target - es.accept_stat);
+        s.log_step = s.mu - s.hbar * sqrt(cnt) / w.gamma;
+        const double mk = pow(cnt, -w.k);
+        s.log_bar = mk * s.log_step + (1.0 - mk) * s.log_bar;
+        s.da_count += 1;
+    }
+    const T* pq = w.V(B2_V_PROPQ, c);
+    if (tune && w.adapt_mass) {                           // quadpotential.py:211-225, 336-350
+        T* var = w.V(B2_V_VAR, c);
+        const int f = s.fg_sel, b = 1 - s.fg_sel;
+        double* fm = w.wv_mean + ((size_t)f * w.C + c) * w.Dp;
+        double* f2 = w.wv_m2 + ((size_t)f * w.C + c) * w.Dp;
+        double* bm = w.wv_mean + ((size_t)b * w.C + c) * w.Dp;
+        double* b2 = w.wv_m2 + ((size_t)b * w.C + c) * w.Dp;
+        const double nf = s.wv_count[f] + 1.0, nb = s.wv_count[b] + 1.0;
+        const bool swap = (s.n_seen > 0) && (s.n_seen % s.window == 0);
+        for (int i = g.lane(); i < w.D; i += G::NT) {
+            const double x = (double)pq[i];
+            double od = x - fm[i];
+            const double m = fm[i] + od / nf;
+            const double r = f2[i] + od * (x - m);
+            var[i] = (T)(r / nf);
+            od = x - bm[i];
+            const double m_b = bm[i] + od / nb;
+            const double r_b = b2[i] + od * (x - m_b);
+            if (swap) { fm[i] = 0.0; f2[i] = 0.0; } else { fm[i] = m; f2[i] = r; }
+            bm[i] = m_b; b2[i] = r_b;
+        }
+        s.wv_count[f] = nf; s.wv_count[b] = nb;
+        if (swap) { s.wv_count[f] = 0.0; s.fg_sel = b; }   // background becomes foreground
+        s.n_seen += 1;
+    }
+    if (!tune) {
+        s.n_post += 1;
+        if (s.diverged) s.n_div_post += 1;
+    }
+    const int row = s.iter - w.iter_base;
+    const size_t o = (size_t)row * w.C + c;
+    if (w.tr_q) {
+        T* dst = w.tr_q + o * w.D;
+        for (int i = g.lane(); i < w.D; i += G::NT) dst[i] = pq[i];
+    }
+    if (g.lane() == 0) {
+        if (w.tr_energy) w.tr_energy[o] = es.energy;
+        if (w.tr_energy_error) w.tr_energy_error[o] = es.energy_error;
+        if (w.tr_model_logp) w.tr_model_logp[o] = es.model_logp;
+        if (w.tr_step_size) w.tr_step_size[o] = exp(s.log_step);           // step_sizes.py:54-58
+        if (w.tr_step_size_bar) w.tr_step_size_bar[o] = exp(s.log_bar);
+        if (w.tr_diverging) w.tr_diverging[o] = (unsigned char)(s.diverged != 0);
+        if (w.tr_tune) w.tr_tune[o] = (unsigned char)tune;
+        if (w.kind == B2_KIND_NUTS) {
+            if (w.tr_max_energy_error) w.tr_max_energy_error[o] = s.max_de;
+            if (w.tr_mean_tree_accept) w.tr_mean_tree_accept[o] = es.accept_stat;
+            if (w.tr_depth) w.tr_depth[o] = s.depth;
+            if (w.tr_tree_size) w.tr_tree_size[o] = s.n_prop;
+        } else {
+            if (w.tr_accept) w.tr_accept[o] = es.accept_stat;
+            if (w.tr_accepted) w.tr_accepted[o] = (unsigned char)es.accepted;
+            if (w.tr_n_steps) w.tr_n_steps[o] = s.hmc_n_steps;
+        }
+    }
+    s.iter += 1;
+    if (s.iter >= w.iter_end) { s.phase = B2_PHASE_DONE; return B2_ACT_NONE; }
+    return B2_ACT_BEGIN_TRANSITION;
+}
+
+// nuts.py:283-309: merge a completed sub-tree (stack level == old depth) into the main tree
+template <typename T, typename G>
+B2_HD int b2_top_merge(const G& g, const B2View<T>& w, int c, B2ChainState& s) {
+    const int d_old = s.depth;
+    const int buf = b2_map_get(s.slot_map, d_old);
+    s.depth += 1;
+    s.n_prop += (1 << d_old);
+    const double sub_ls = s.lv_log_size[buf];
+    const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_TOP, (uint32_t)d_old, 0u);
+    if (log(u) < sub_ls - s.log_size) {                   // nuts.py:289-291
+        b2_copy(g, w.D, w.V(B2_V_PROPQ, c), w.S(buf, B2_S_Q, c));
+        b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.S(buf, B2_S_G, c));
+        s.prop_energy = s.lv_energy[buf];
+        s.prop_logp = s.lv_logp[buf];
+    }
+    s.log_size = b2_logaddexp(s.log_size, sub_ls);
+    s.log_accept = b2_logaddexp(s.log_accept, s.lv_log_accept[buf]);
+    const T* var = w.V(B2_V_VAR, c);
+    T* psum = w.V(B2_V_PSUM, c);
+    // dir=1: main tree | new sub-tree.   dir=0: new sub-tree (reversed in time) | main tree.
+    const T* first1 = s.dir ? w.V(B2_V_PE0, c) : w.S(buf, B2_S_PLAST, c);
+    const T* last1 = s.dir ? w.V(B2_V_POLD, c) : w.S(buf, B2_S_PFIRST, c);
+    const T* psum1 = s.dir ? psum : w.S(buf, B2_S_PSUM, c);
+    const T* first2 = s.dir ? w.S(buf, B2_S_PFIRST, c) : w.V(B2_V_POLD, c);
+    const T* last2 = s.dir ? w.S(buf, B2_S_PLAST, c) : w.V(B2_V_PE1, c);
+    const T* psum2 = s.dir ? w.S(buf, B2_S_PSUM, c) : psum;
+    const bool turning = b2_uturn<T, G>(g, w.D, var, first1, last1, psum1, first2, last2, psum2, true, psum, (T*)0);
+    if (turning) { s.turned = 1; return B2_ACT_END_NUTS; }
+    if (s.depth >= s.max_depth) return B2_ACT_END_NUTS_MAXDEPTH;
+    return B2_ACT_BEGIN_DOUBLING;
+}
+
+// nuts.py:311-345 then the binary-counter form of nuts.py:347-389
+template <typename T, typename G>
+B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s, double logp_new) {
+    const int e = s.dir;
+    const double energy = b2_finish_leapfrog(g, w, c, e, e ? s.eps : -s.eps, logp_new);
+    s.n_grad += 1;
+    double de = energy - s.e0;
+    if (de != de) de = INFINITY;                          // nuts.py:322-323
+    if (fabs(de) > fabs(s.max_de)) s.max_de = de;
+    if (!(fabs(de) < w.emax)) {                           // divergence, nuts.py:338-345
+        s.diverged = 1;
+        s.depth += 1;
+        s.n_prop += s.leaf_n + 1;
+        return B2_ACT_END_NUTS;
+    }
+    const double leaf_ls = -de;
+    const double leaf_la = -de + (-de < 0.0 ? -de : 0.0);  // nuts.py:331 (sic)
+    const T* qe = w.V(B2_V_QE0 + e, c);
+    const T* pe = w.V(B2_V_PE0 + e, c);
+    const T* ge = w.V(B2_V_GE0 + e, c);
+    const T* var = w.V(B2_V_VAR, c);
+    const int n = s.leaf_n;
+    int j = 0;
+    while ((n >> j) & 1) ++j;                             // trailing ones = number of merges
+    if (j == 0) {
+        const int buf = b2_map_get(s.slot_map, 0);
+        T *sf = w.S(buf, B2_S_PFIRST, c), *sl = w.S(buf, B2_S_PLAST, c), *ss = w.S(buf, B2_S_PSUM, c);
+        T *sq = w.S(buf, B2_S_Q, c), *sg = w.S(buf, B2_S_G, c);
+        for (int i = g.lane(); i < w.D; i += G::NT) {
+            const T p = pe[i];
+            sf[i] = p; sl[i] = p; ss[i] = p; sq[i] = qe[i]; sg[i] = ge[i];
+        }
+        s.lv_log_size[buf] = leaf_ls; s.lv_log_accept[buf] = leaf_la;
+        s.lv_energy[buf] = energy; s.lv_logp[buf] = logp_new;
+    } else {
+        for (int k = 0; k < j; ++k) {
+            const int b1 = b2_map_get(s.slot_map, k);
+            const int b2i = b2_map_get(s.slot_map, k > 0 ? k - 1 : 0);
+            const bool leaf2 = (k == 0);
+            const T* f2 = leaf2 ? pe : w.S(b2i, B2_S_PFIRST, c);
+            const T* l2 = leaf2 ? pe : w.S(b2i, B2_S_PLAST, c);
+            const T* s2 = leaf2 ? pe : w.S(b2i, B2_S_PSUM, c);
+            const T* q2 = leaf2 ? qe : w.S(b2i, B2_S_Q, c);
+            const T* g2 = leaf2 ? ge : w.S(b2i, B2_S_G, c);
+            const double ls2 = leaf2 ? leaf_ls : s.lv_log_size[b2i];
+            const double la2 = leaf2 ? leaf_la : s.lv_log_accept[b2i];
+            const double en2 = leaf2 ? energy : s.lv_energy[b2i];
+            const double lp2 = leaf2 ? logp_new : s.lv_logp[b2i];
+            T *f1 = w.S(b1, B2_S_PFIRST, c), *l1 = w.S(b1, B2_S_PLAST, c), *s1 = w.S(b1, B2_S_PSUM, c);
+            const bool turning = b2_uturn<T, G>(g, w.D, var, f1, l1, s1, f2, l2, s2, k > 0, s1, l1);
+            if (turning) { s.turned = 1; break; }
+            const double ls1 = s.lv_log_size[b1];
+            const double ls = b2_logaddexp(ls1, ls2);
+            const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_MERGE, (uint32_t)s.depth,
+                                        ((uint32_t)(k + 1) << 16) | (uint32_t)n);
+            if (log(u) < ls2 - ls) {                      // nuts.py:375-378
+                b2_copy(g, w.D, w.S(b1, B2_S_Q, c), q2);
+                b2_copy(g, w.D, w.S(b1, B2_S_G, c), g2);
+                s.lv_energy[b1] = en2; s.lv_logp[b1] = lp2;
+            }
+            s.lv_log_size[b1] = ls;
+            s.lv_log_accept[b1] = b2_logaddexp(s.lv_log_accept[b1], la2);
+        }
+        if (s.turned) {
+            s.depth += 1;
+            s.n_prop += n + 1;
+            return B2_ACT_END_NUTS;
+        }
+        s.slot_map = b2_map_swap(s.slot_map, j, j - 1);
+    }
+    s.leaf_n = n + 1;
+    if (s.leaf_n == (1 << s.depth)) return B2_ACT_TOP_MERGE;
+    b2_prepare_leapfrog(g, w, c, e, e ? s.eps : -s.eps);
+    return B2_ACT_NONE;
+}
+
+// hmc.py:110-152
+template <typename T, typename G>
+B2_HD int b2_finish_hmc_step(const G& g, const B2View<T>& w, int c, B2ChainState& s, double logp_new, B2EndStats& es) {
+    const double energy = b2_finish_leapfrog(g, w, c, 1, s.eps, logp_new);
+    s.n_grad += 1;
+    s.hmc_step += 1;
+    if (s.hmc_step < s.hmc_n_steps) { b2_prepare_leapfrog(g, w, c, 1, s.eps); return B2_ACT_NONE; }
+    bool div = !b2_finite(energy);                        // :123-125
+    double de = s.e0 - energy;
+    if (de != de) de = -INFINITY;
+    if (fabs(de) > w.emax) div = true;                    // :129
+    const double ex = exp(de);
+    const double accept = ex < 1.0 ? ex : 1.0;
+    bool accepted = false;
+    if (!div) {
+        const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_HMC_ACCEPT, 0u, 0u);
+        accepted = !(u >= accept);                        // :136
+    }
+    s.diverged = div ? 1 : 0;
+    if (accepted) {
+        b2_copy(g, w.D, w.V(B2_V_PROPQ, c), w.V(B2_V_QE1, c));
+        b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.V(B2_V_GE1, c));
+        s.cur_logp = logp_new;
+    }
+    es.accept_stat = accept; es.energy = energy; es.energy_error = de; es.model_logp = logp_new;
+    es.accepted = accepted;
+    return B2_ACT_END;
+}
+
+// One unit of progress for chain c.  Returns true while the chain still needs gradients.
+template <typename T, typename G>
+B2_HD bool b2_advance(const G& g, const B2View<T>& w, int c, B2ChainState& s, double logp_new) {
+    int act = B2_ACT_NONE;
+    B2EndStats es = {0.0, 0.0, 0.0, 0.0, true};
+    if (s.phase == B2_PHASE_INIT) {
+        s.cur_logp = logp_new;
+        s.n_grad += 1;
+        b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.V(B2_V_GE1, c));
+        if (s.iter >= w.iter_end) s.phase = B2_PHASE_DONE;
+        else act = B2_ACT_BEGIN_TRANSITION;
+    } else if (s.phase == B2_PHASE_TREE) {
+        act = b2_finish_leaf(g, w, c, s, logp_new);
+    } else if (s.phase == B2_PHASE_HMC) {
+        act = b2_finish_hmc_step(g, w, c, s, logp_new, es);
+    }
+    if (act == B2_ACT_TOP_MERGE) act = b2_top_merge(g, w, c, s);
+    if (act == B2_ACT_END_NUTS || act == B2_ACT_END_NUTS_MAXDEPTH) {
+        es.accept_stat = 0.0;                             // nuts.py:391-397
+        if (s.log_size > 0.0) es.accept_stat = exp(s.log_accept) / expm1(s.log_size);
+        if (act == B2_ACT_END_NUTS_MAXDEPTH && !(s.iter < w.tune_until)) s.n_maxdepth_post += 1;   // nuts.py:182-184
+        s.cur_logp = s.prop_logp;
+        es.energy = s.prop_energy; es.energy_error = s.prop_energy - s.e0; es.model_logp = s.prop_logp;
+        act = B2_ACT_END;
+    }
+    if (act == B2_ACT_END) act = b2_end_transition(g, w, c, s, es);
+    if (act == B2_ACT_BEGIN_TRANSITION) act = b2_begin_transition(g, w, c, s);
+    if (act == B2_ACT_BEGIN_DOUBLING) b2_begin_doubling(g, w, c, s);
+    return s.phase == B2_PHASE_TREE || s.phase == B2_PHASE_HMC;
+}

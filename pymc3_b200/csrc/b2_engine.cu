@@ -1,0 +1,464 @@
+// libb200nuts.so -- engine lifecycle, kernels that wrap the shared state machine, C ABI.
+//
+// Execution modes
+//   persistent : one launch runs every chain's whole run; a warp (D <= B2_WARP_MAX_D) or a
+//                block (larger D) owns a chain and loops {model logp+grad, advance}.  Used
+//                when a chain's likelihood is cheap enough for one group (eight schools,
+//                stochastic volatility, small-N GLM / hierarchical).
+//   lock-step  : all chains advance one leapfrog per step: {chain-batched likelihood kernel,
+//                advance kernel}; chains are asynchronous across *transitions* (a chain that
+//                ends its tree starts the next one in the same step), so the batch stays full.
+//
+// Reference seams replaced: see include/b200nuts.h.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "b2_engine.cuh"
+
+static thread_local std::string g_last_error;
+void b2_set_error(const std::string& msg) { g_last_error = msg; }
+
+#define B2_WARP_MAX_D 1024
+#define B2_BLOCK_NT 256
+#define B2_WARPS_PER_BLOCK 4
+
+// ------------------------------------------------------------------------------- kernels
+template <typename T>
+__global__ void k_init_chains(B2View<T> w, const T* q0, const unsigned long long* seeds, double step0,
+                              const double* mass_mean, const double* mass_var, double mass_weight,
+                              int window, int iter0) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= w.C) return;
+    B2WarpGroup g;
+    B2ChainState s;
+    b2_init_chain<T, B2WarpGroup>(g, w, c, s, q0 + (size_t)c * w.D, seeds[c], step0, mass_mean, mass_var,
+                                  mass_weight, window, iter0);
+    if (g.lane() == 0) w.st[c] = s;
+}
+
+__device__ __forceinline__ bool b2_needs_grad(int phase) {
+    return phase == B2_PHASE_INIT || phase == B2_PHASE_TREE || phase == B2_PHASE_HMC;
+}
+
+// group-per-chain likelihood (parity hook, small models in lock-step mode, cross-check)
+template <typename T, typename G>
+__device__ __forceinline__ void logp_group_body(const G& g, const B2ModelData& m, const T* qA, const T* qB,
+                                                T* gA, T* gB, int ld, const B2ChainState* st, int c,
+                                                double* logp) {
+    int sel = 0;
+    if (st) {
+        if (!b2_needs_grad(st[c].phase)) return;
+        sel = st[c].sel;
+    }
+    const T* q = (sel ? qB : qA) + (size_t)c * ld;
+    T* gr = (sel ? gB : gA) + (size_t)c * ld;
+    const double lp = b2_eval_model<T, G>(g, m, q, gr, c);
+    if (g.lane() == 0) logp[c] = lp;
+}
+
+template <typename T>
+__global__ void k_logp_warp(B2ModelData m, const T* qA, const T* qB, T* gA, T* gB, int ld,
+                            const B2ChainState* st, int n, double* logp) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    B2WarpGroup g;
+    logp_group_body<T, B2WarpGroup>(g, m, qA, qB, gA, gB, ld, st, c, logp);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B2_BLOCK_NT) k_logp_block(B2ModelData m, const T* qA, const T* qB, T* gA, T* gB,
+                                                            int ld, const B2ChainState* st, int n, double* logp) {
+    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
+    B2BlockGroup<B2_BLOCK_NT> g;
+    g.red = red;
+    logp_group_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, m, qA, qB, gA, gB, ld, st, blockIdx.x, logp);
+}
+
+template <typename T>
+__global__ void k_advance_warp(B2View<T> w) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= w.C) return;
+    B2WarpGroup g;
+    B2ChainState s = w.st[c];
+    if (!b2_needs_grad(s.phase)) return;
+    b2_advance<T, B2WarpGroup>(g, w, c, s, w.logp_eval[c]);
+    if (g.lane() == 0) w.st[c] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w) {
+    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
+    B2BlockGroup<B2_BLOCK_NT> g;
+    g.red = red;
+    const int c = blockIdx.x;
+    B2ChainState s = w.st[c];
+    if (!b2_needs_grad(s.phase)) return;
+    b2_advance<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, c, s, w.logp_eval[c]);
+    if (g.lane() == 0) w.st[c] = s;
+}
+
+template <typename T, typename G>
+__device__ __forceinline__ void persistent_body(const G& g, const B2View<T>& w, const B2ModelData& m, int c) {
+    B2ChainState s = w.st[c];
+    bool active = b2_needs_grad(s.phase);
+    while (active) {
+        const T* q = w.V(B2_V_QE0 + s.sel, c);
+        T* gr = w.V(B2_V_GE0 + s.sel, c);
+        g.sync();
+        const double lp = b2_eval_model<T, G>(g, m, q, gr, c);
+        g.sync();
+        active = b2_advance<T, G>(g, w, c, s, lp);
+    }
+    if (g.lane() == 0) w.st[c] = s;
+}
+
+template <typename T>
+__global__ void k_persistent_warp(B2View<T> w, B2ModelData m) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= w.C) return;
+    B2WarpGroup g;
+    persistent_body<T, B2WarpGroup>(g, w, m, c);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B2_BLOCK_NT) k_persistent_block(B2View<T> w, B2ModelData m) {
+    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
+    B2BlockGroup<B2_BLOCK_NT> g;
+    g.red = red;
+    persistent_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, m, blockIdx.x);
+}
+
+__global__ void k_count_active(const B2ChainState* st, int C, int* out) {
+    int n = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x)
+        n += b2_needs_grad(st[c].phase) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+
+// ------------------------------------------------------------------------------ helpers
+static size_t dsize(int dtype) { return dtype == B2_F64 ? 8 : 4; }
+
+template <typename T>
+static B2View<T> make_view(b2_engine* e) {
+    B2View<T> w;
+    memset(&w, 0, sizeof(w));
+    w.C = e->C; w.D = e->D; w.Dp = e->Dp;
+    w.vec = (T*)e->vec; w.wv_mean = e->wv_mean; w.wv_m2 = e->wv_m2; w.st = e->st; w.logp_eval = e->logp_eval;
+    return w;
+}
+
+static bool use_block_group(const b2_engine* e) { return e->D > B2_WARP_MAX_D; }
+
+static int ensure_glm_scratch(b2_engine* e) {
+    if (e->md.family != B2_FAMILY_GLM_LOGIT || e->glm_scratch) return 0;
+    const size_t bytes = (size_t)e->C * e->md.N * dsize(e->dtype);
+    if (bytes > ((size_t)8 << 30)) {
+        b2_set_error("group GLM evaluator needs C*N scratch > 8 GiB; use the SIMT/tcgen05 path");
+        return -5;
+    }
+    B2_CUDA_OK(cudaMalloc(&e->glm_scratch, bytes));
+    e->md.scratch = e->glm_scratch;
+    return 0;
+}
+
+// group evaluator for n points (planes A/B of row stride ld)
+template <typename T>
+static int launch_logp_group(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
+                             const B2ChainState* st, int n, double* logp, cudaStream_t s) {
+    int rc = ensure_glm_scratch(e);
+    if (rc) return rc;
+    if (use_block_group(e)) {
+        k_logp_block<T><<<n, B2_BLOCK_NT, 0, s>>>(e->md, qA, qB, gA, gB, ld, st, n, logp);
+    } else {
+        const int nb = (n + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
+        k_logp_warp<T><<<nb, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(e->md, qA, qB, gA, gB, ld, st, n, logp);
+    }
+    e->launches += 1;
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int pick_glm_path(const b2_engine* e, int requested) {
+    if (e->md.family != B2_FAMILY_GLM_LOGIT) return B2_GLM_GROUP;
+    if (requested == B2_GLM_AUTO) {
+        if (e->dtype == B2_F32 && b2_glm_tc_supported(e)) return B2_GLM_TCGEN05;
+        return ((size_t)e->md.N * e->C >= (size_t)1 << 16) ? B2_GLM_SIMT : B2_GLM_GROUP;
+    }
+    return requested;
+}
+
+// one likelihood evaluation for every chain, dispatching to the best kernel for the family
+template <typename T>
+static int launch_likelihood(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
+                             const B2ChainState* st, int n, double* logp, int glm_path, cudaStream_t s);
+
+template <>
+int launch_likelihood<float>(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
+                             const B2ChainState* st, int n, double* logp, int glm_path, cudaStream_t s) {
+    if (e->md.family == B2_FAMILY_GLM_LOGIT) {
+        const int path = pick_glm_path(e, glm_path);
+        if (path == B2_GLM_TCGEN05) {
+            if (!b2_glm_tc_supported(e)) { b2_set_error("tcgen05 GLM path does not support this shape"); return -6; }
+            return b2_glm_tc_launch(e, qA, qB, gA, gB, ld, st, n, logp, s);
+        }
+        if (path == B2_GLM_SIMT) return b2_glm_simt_launch<float>(e, qA, qB, gA, gB, ld, st, n, logp, s);
+    }
+    if (e->md.family == B2_FAMILY_HIER_LINEAR_NCP && (size_t)e->md.N * n >= (size_t)1 << 22)
+        return b2_hier_launch<float>(e, qA, qB, gA, gB, ld, st, n, logp, s);
+    return launch_logp_group<float>(e, qA, qB, gA, gB, ld, st, n, logp, s);
+}
+
+template <>
+int launch_likelihood<double>(b2_engine* e, const double* qA, const double* qB, double* gA, double* gB, int ld,
+                              const B2ChainState* st, int n, double* logp, int glm_path, cudaStream_t s) {
+    if (e->md.family == B2_FAMILY_GLM_LOGIT) {
+        const int path = pick_glm_path(e, glm_path);
+        if (path == B2_GLM_TCGEN05) { b2_set_error("tcgen05 GLM path is fp32-only (use B2_F32)"); return -6; }
+        if (path == B2_GLM_SIMT) return b2_glm_simt_launch<double>(e, qA, qB, gA, gB, ld, st, n, logp, s);
+    }
+    if (e->md.family == B2_FAMILY_HIER_LINEAR_NCP && (size_t)e->md.N * n >= (size_t)1 << 22)
+        return b2_hier_launch<double>(e, qA, qB, gA, gB, ld, st, n, logp, s);
+    return launch_logp_group<double>(e, qA, qB, gA, gB, ld, st, n, logp, s);
+}
+
+// ------------------------------------------------------------------------------- C ABI
+extern "C" int b2_abi_version(void) { return B2_ABI_VERSION; }
+extern "C" const char* b2_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int b2_engine_create(const b2_model_desc* desc, int32_t n_chains, int32_t dtype, int32_t device,
+                                b2_engine** out) {
+    if (!desc || !out || n_chains <= 0) { b2_set_error("b2_engine_create: bad arguments"); return -1; }
+    if (dtype != B2_F32 && dtype != B2_F64) { b2_set_error("b2_engine_create: dtype must be B2_F32 or B2_F64"); return -2; }
+    int expect_D = -1;
+    switch (desc->family) {
+    case B2_STD_NORMAL: expect_D = desc->D; break;
+    case B2_EIGHT_SCHOOLS_NCP: expect_D = desc->N + 2; break;
+    case B2_GLM_LOGIT: expect_D = desc->G + 1; break;
+    case B2_HIER_LINEAR_NCP: expect_D = 2 * desc->G + 5; break;
+    case B2_STOCH_VOL: expect_D = desc->N + 2; break;
+    default: b2_set_error("b2_engine_create: unknown model family"); return -3;
+    }
+    if (desc->D != expect_D || desc->D <= 0) { b2_set_error("b2_engine_create: D inconsistent with family/shape"); return -4; }
+    int count = 0;
+    B2_CUDA_OK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { b2_set_error("b2_engine_create: no such CUDA device"); return -7; }
+    B2_CUDA_OK(cudaSetDevice(device));
+    b2_engine* e = new b2_engine();
+    memset(e, 0, sizeof(*e));
+    e->desc = *desc;
+    e->C = n_chains; e->D = desc->D; e->Dp = (desc->D + 3) & ~3; e->dtype = dtype; e->device = device;
+    e->md.family = desc->family; e->md.D = desc->D; e->md.N = desc->N; e->md.G = desc->G;
+    e->md.aux0 = desc->d_aux0; e->md.aux1 = desc->d_aux1; e->md.X = desc->d_X; e->md.yf = desc->d_y;
+    e->md.floor_u8 = desc->d_floor; e->md.grp_off = desc->d_grp_off; e->md.scratch = nullptr;
+    for (int i = 0; i < 4; ++i) e->md.hp[i] = desc->hp[i];
+    cudaDeviceProp prop;
+    B2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    const size_t nvec = (size_t)B2_NUM_VEC_SLOTS * e->C * e->Dp;
+    B2_CUDA_OK(cudaMalloc(&e->vec, nvec * dsize(dtype)));
+    B2_CUDA_OK(cudaMemset(e->vec, 0, nvec * dsize(dtype)));
+    B2_CUDA_OK(cudaMalloc(&e->wv_mean, (size_t)2 * e->C * e->Dp * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&e->wv_m2, (size_t)2 * e->C * e->Dp * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&e->st, (size_t)e->C * sizeof(B2ChainState)));
+    B2_CUDA_OK(cudaMemset(e->st, 0, (size_t)e->C * sizeof(B2ChainState)));
+    B2_CUDA_OK(cudaMalloc(&e->logp_eval, (size_t)e->C * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&e->d_active, sizeof(int)));
+    B2_CUDA_OK(cudaMallocHost(&e->h_active, sizeof(int)));
+    *out = e;
+    return 0;
+}
+
+extern "C" int b2_engine_destroy(b2_engine* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaFree(e->vec); cudaFree(e->wv_mean); cudaFree(e->wv_m2); cudaFree(e->st); cudaFree(e->logp_eval);
+    cudaFree(e->glm_scratch); cudaFree(e->d_active); cudaFree(e->glm_ws); cudaFree(e->hier_ws);
+    cudaFreeHost(e->h_active);
+    delete e;
+    return 0;
+}
+
+extern "C" int b2_logp_dlogp(b2_engine* e, const void* d_q, int32_t n_points, double* d_logp, void* d_grad,
+                             int32_t glm_path, void* stream) {
+    if (!e || !d_q || !d_logp || !d_grad) { b2_set_error("b2_logp_dlogp: null argument"); return -1; }
+    if (n_points <= 0 || n_points > e->C) { b2_set_error("b2_logp_dlogp: n_points must be in [1, n_chains]"); return -2; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (e->dtype == B2_F64)
+        return launch_likelihood<double>(e, (const double*)d_q, (const double*)d_q, (double*)d_grad, (double*)d_grad,
+                                         e->D, nullptr, n_points, d_logp, glm_path, s);
+    return launch_likelihood<float>(e, (const float*)d_q, (const float*)d_q, (float*)d_grad, (float*)d_grad,
+                                    e->D, nullptr, n_points, d_logp, glm_path, s);
+}
+
+template <typename T>
+static int set_state_t(b2_engine* e, const void* d_q0, const uint64_t* d_seeds, double step0,
+                       const double* mm, const double* mv, double mw, int window, cudaStream_t s) {
+    B2View<T> w = make_view<T>(e);
+    const int nb = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
+    k_init_chains<T><<<nb, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, (const T*)d_q0, (const unsigned long long*)d_seeds,
+                                                            step0, mm, mv, mw, window, 0);
+    e->launches += 1;
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2_set_state(b2_engine* e, const void* d_q0, const uint64_t* d_seeds, double step_size0,
+                            const double* d_mass_mean, const double* d_mass_var, double mass_weight,
+                            int32_t adaptation_window, void* stream) {
+    if (!e || !d_q0 || !d_seeds || !d_mass_mean || !d_mass_var) { b2_set_error("b2_set_state: null argument"); return -1; }
+    if (!(step_size0 > 0) || adaptation_window <= 0) { b2_set_error("b2_set_state: step size and window must be > 0"); return -2; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    int rc = e->dtype == B2_F64
+                 ? set_state_t<double>(e, d_q0, d_seeds, step_size0, d_mass_mean, d_mass_var, mass_weight, adaptation_window, (cudaStream_t)stream)
+                 : set_state_t<float>(e, d_q0, d_seeds, step_size0, d_mass_mean, d_mass_var, mass_weight, adaptation_window, (cudaStream_t)stream);
+    if (rc) return rc;
+    e->iter_done = 0;
+    e->state_set = true;
+    return 0;
+}
+
+template <typename T>
+__global__ void k_set_position(B2View<T> w, const T* q) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)w.C * w.D) return;
+    const int c = (int)(idx / w.D), i = (int)(idx - (size_t)c * w.D);
+    w.V(B2_V_PROPQ, c)[i] = q[idx];
+    w.V(B2_V_QE1, c)[i] = q[idx];
+    if (i == 0 && w.st[c].phase != B2_PHASE_FAILED) { w.st[c].phase = B2_PHASE_INIT; w.st[c].sel = 1; }
+}
+
+extern "C" int b2_set_position(b2_engine* e, const void* d_q, void* stream) {
+    if (!e || !d_q) { b2_set_error("b2_set_position: null argument"); return -1; }
+    if (!e->state_set) { b2_set_error("b2_set_position: call b2_set_state first"); return -2; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->C * e->D;
+    const int nb = (int)((n + 255) / 256);
+    if (e->dtype == B2_F64) k_set_position<double><<<nb, 256, 0, (cudaStream_t)stream>>>(make_view<double>(e), (const double*)d_q);
+    else k_set_position<float><<<nb, 256, 0, (cudaStream_t)stream>>>(make_view<float>(e), (const float*)d_q);
+    e->launches += 1;
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static bool persistent_ok(const b2_engine* e) {
+    switch (e->md.family) {
+    case B2_FAMILY_STD_NORMAL:
+    case B2_FAMILY_EIGHT_SCHOOLS_NCP:
+    case B2_FAMILY_STOCH_VOL:
+        return true;
+    case B2_FAMILY_GLM_LOGIT:
+        return (size_t)e->md.N * (e->md.G + 1) <= (size_t)1 << 16;     // one warp can afford the whole likelihood
+    case B2_FAMILY_HIER_LINEAR_NCP:
+        return e->md.N <= 1 << 14;
+    }
+    return false;
+}
+
+template <typename T>
+static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr, cudaStream_t s) {
+    B2View<T> w = make_view<T>(e);
+    w.kind = o->kind;
+    w.iter_base = e->iter_done; w.iter_end = e->iter_done + o->n_iters; w.tune_until = o->tune_until;
+    w.max_treedepth = o->max_treedepth; w.early_max_treedepth = o->early_max_treedepth;
+    w.emax = o->Emax; w.target = o->target_accept; w.gamma = o->gamma; w.k = o->k; w.t0 = o->t0;
+    w.adapt_step = o->adapt_step_size; w.adapt_mass = o->adapt_mass;
+    w.path_length = o->path_length; w.max_steps = o->max_steps; w.hmc_jitter = o->hmc_jitter;
+    if (tr) {
+        w.tr_q = (T*)tr->d_q; w.tr_energy = tr->d_energy; w.tr_energy_error = tr->d_energy_error;
+        w.tr_max_energy_error = tr->d_max_energy_error; w.tr_mean_tree_accept = tr->d_mean_tree_accept;
+        w.tr_step_size = tr->d_step_size; w.tr_step_size_bar = tr->d_step_size_bar; w.tr_model_logp = tr->d_model_logp;
+        w.tr_accept = tr->d_accept; w.tr_depth = tr->d_depth; w.tr_tree_size = tr->d_tree_size; w.tr_n_steps = tr->d_n_steps;
+        w.tr_diverging = tr->d_diverging; w.tr_tune = tr->d_tune; w.tr_accepted = tr->d_accepted;
+    }
+    int mode = o->exec_mode;
+    if (mode == B2_EXEC_AUTO) mode = persistent_ok(e) ? B2_EXEC_PERSISTENT : B2_EXEC_LOCKSTEP;
+    if (mode == B2_EXEC_PERSISTENT && e->md.family == B2_FAMILY_GLM_LOGIT) {
+        int rc = ensure_glm_scratch(e);
+        if (rc) return rc;
+    }
+    const bool blk = use_block_group(e);
+    const int nb_warp = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
+    if (mode == B2_EXEC_PERSISTENT) {
+        if (blk) k_persistent_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, e->md);
+        else k_persistent_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, e->md);
+        e->launches += 1;
+        B2_CUDA_OK(cudaGetLastError());
+        B2_CUDA_OK(cudaStreamSynchronize(s));
+    } else {
+        const T* qA = w.V(B2_V_QE0, 0); const T* qB = w.V(B2_V_QE1, 0);
+        T* gA = w.V(B2_V_GE0, 0); T* gB = w.V(B2_V_GE1, 0);
+        const int batch = 32;
+        for (;;) {
+            for (int b = 0; b < batch; ++b) {
+                int rc = launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
+                if (rc) return rc;
+                if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w);
+                else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w);
+                e->launches += 1;
+            }
+            B2_CUDA_OK(cudaMemsetAsync(e->d_active, 0, sizeof(int), s));
+            k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, e->d_active);
+            e->launches += 1;
+            B2_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+            B2_CUDA_OK(cudaStreamSynchronize(s));
+            if (*e->h_active == 0) break;
+        }
+        B2_CUDA_OK(cudaGetLastError());
+    }
+    e->iter_done += o->n_iters;
+    return 0;
+}
+
+extern "C" int b2_sample_run(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* trace, void* stream) {
+    if (!e || !o) { b2_set_error("b2_sample_run: null argument"); return -1; }
+    if (!e->state_set) { b2_set_error("b2_sample_run: call b2_set_state first"); return -2; }
+    if (o->n_iters <= 0) { b2_set_error("b2_sample_run: n_iters must be > 0"); return -3; }
+    if (o->kind != B2_NUTS && o->kind != B2_HMC) { b2_set_error("b2_sample_run: unknown sampler kind"); return -4; }
+    if (o->kind == B2_NUTS && (o->max_treedepth < 1 || o->max_treedepth > B2_MAX_LEVELS ||
+                               o->early_max_treedepth < 1 || o->early_max_treedepth > B2_MAX_LEVELS)) {
+        b2_set_error("b2_sample_run: tree depths must be in [1, 12]");
+        return -5;
+    }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    return e->dtype == B2_F64 ? run_t<double>(e, o, trace, (cudaStream_t)stream)
+                              : run_t<float>(e, o, trace, (cudaStream_t)stream);
+}
+
+extern "C" int b2_get_chain_reports(b2_engine* e, b2_chain_report* out) {
+    if (!e || !out) { b2_set_error("b2_get_chain_reports: null argument"); return -1; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    std::vector<B2ChainState> h(e->C);
+    B2_CUDA_OK(cudaMemcpy(h.data(), e->st, (size_t)e->C * sizeof(B2ChainState), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < e->C; ++c) {
+        out[c].phase = h[c].phase; out[c].fail_code = h[c].fail_code; out[c].iter = h[c].iter;
+        out[c].n_div_post = h[c].n_div_post; out[c].n_maxdepth_post = h[c].n_maxdepth_post;
+        out[c].n_post = h[c].n_post; out[c].n_grad = h[c].n_grad;
+        out[c].step_size = exp(h[c].log_step); out[c].step_size_bar = exp(h[c].log_bar);
+    }
+    return 0;
+}
+
+template <typename T>
+static int get_vec_t(b2_engine* e, int slot, double* out) {
+    std::vector<T> h((size_t)e->C * e->Dp);
+    B2_CUDA_OK(cudaMemcpy(h.data(), (T*)e->vec + (size_t)slot * e->C * e->Dp, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < e->C; ++c)
+        for (int i = 0; i < e->D; ++i) out[(size_t)c * e->D + i] = (double)h[(size_t)c * e->Dp + i];
+    return 0;
+}
+
+extern "C" int b2_get_mass_var(b2_engine* e, double* out) {
+    if (!e || !out) { b2_set_error("b2_get_mass_var: null argument"); return -1; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    return e->dtype == B2_F64 ? get_vec_t<double>(e, B2_V_VAR, out) : get_vec_t<float>(e, B2_V_VAR, out);
+}
+
+extern "C" int b2_get_position(b2_engine* e, double* out) {
+    if (!e || !out) { b2_set_error("b2_get_position: null argument"); return -1; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    return e->dtype == B2_F64 ? get_vec_t<double>(e, B2_V_PROPQ, out) : get_vec_t<float>(e, B2_V_PROPQ, out);
+}
+
+extern "C" int64_t b2_kernel_launches(b2_engine* e) { return e ? e->launches : 0; }

@@ -1,0 +1,51 @@
+// Engine object shared by the .cu translation units of libb200nuts.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/b200nuts.h"
+#include "b2_models.cuh"
+
+struct b2_engine {
+    b2_model_desc desc;
+    B2ModelData md;
+    int C, D, Dp, dtype, device;
+    void* vec;                 // [B2_NUM_VEC_SLOTS][C][Dp] of dtype
+    double* wv_mean;           // [2][C][Dp]
+    double* wv_m2;
+    B2ChainState* st;          // [C]
+    double* logp_eval;         // [C]
+    void* glm_scratch;         // lazily allocated [C][N] for the group evaluator
+    int* d_active;             // device counter
+    int* h_active;             // pinned host mirror
+    void* glm_ws;              // workspace of the chain-batched GLM kernels (b2_glm_*.cu)
+    size_t glm_ws_bytes;
+    void* hier_ws;             // workspace of the chain-batched hierarchical kernel
+    size_t hier_ws_bytes;
+    int iter_done;             // iterations completed by every chain so far
+    bool state_set;
+    int64_t launches;
+    int sm_count;
+};
+
+void b2_set_error(const std::string& msg);
+#define B2_CUDA_OK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            b2_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            return (int)_e;                                                                \
+        }                                                                                  \
+    } while (0)
+
+// chain-batched likelihood kernels (one launch evaluates every chain's pending position)
+// q/g planes: edge 0 at plane pointers A, edge 1 at B; st selects per chain (null -> plane A).
+template <typename T>
+int b2_glm_simt_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
+                       const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);
+int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
+                     const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);
+bool b2_glm_tc_supported(const b2_engine* e);
+template <typename T>
+int b2_hier_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
+                   const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);

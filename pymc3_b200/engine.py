@@ -1,0 +1,145 @@
+"""Python handle on one device engine (one per GPU).  Plumbing only: PyTorch owns the device
+buffers, ctypes calls libb200nuts.so; no arithmetic of the hot path happens here.
+
+Mirrors the runtime half of the reference's model->array bridge
+(pymc3/model.py:541-713 ValueGradFunction) plus the draw loop's state
+(pymc3/sampling.py:847-936), batched over chains.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+_NUTS_STATS = {"energy": "f8", "energy_error": "f8", "max_energy_error": "f8", "mean_tree_accept": "f8",
+               "step_size": "f8", "step_size_bar": "f8", "model_logp": "f8", "depth": "i4",
+               "tree_size": "i4", "diverging": "u1", "tune": "u1"}
+_HMC_STATS = {"energy": "f8", "energy_error": "f8", "step_size": "f8", "step_size_bar": "f8",
+              "model_logp": "f8", "accept": "f8", "n_steps": "i4", "diverging": "u1", "tune": "u1",
+              "accepted": "u1"}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _capi.B2Error("pymc3_b200 needs a CUDA device: the NUTS/HMC hot path has no CPU fallback")
+    return torch
+
+
+class Engine:
+    """`n_chains` chains of one model family on one CUDA device."""
+
+    def __init__(self, desc_builder, n_chains, dtype="float32", device=0):
+        torch = _torch()
+        self.torch = torch
+        self.lib = _capi.load_library()
+        self.device = int(device)
+        self.dev = torch.device("cuda", self.device)
+        self.n_chains = int(n_chains)
+        self.np_dtype = np.dtype(dtype)
+        if self.np_dtype not in (np.dtype("float32"), np.dtype("float64")):
+            raise TypeError("Invalid dtype %s: engine vectors are float32 or float64" % dtype)
+        self.t_dtype = torch.float64 if self.np_dtype == np.float64 else torch.float32
+        self._keep = []                       # device tensors referenced by raw pointer
+        self.desc = desc_builder(self._upload)
+        self.D = int(self.desc.D)
+        handle = C.c_void_p()
+        _capi.check(self.lib.b2_engine_create(C.byref(self.desc), self.n_chains,
+                                              _capi.B2_F64 if self.np_dtype == np.float64 else _capi.B2_F32,
+                                              self.device, C.byref(handle)), self.lib)
+        self.handle = handle
+        self.iter_done = 0
+
+    # -- plumbing
+    def _upload(self, array, dtype):
+        t = self.torch.as_tensor(np.ascontiguousarray(array, dtype=dtype), device=self.dev)
+        self._keep.append(t)
+        return t.data_ptr()
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.b2_engine_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- ValueGradFunction.__call__ for a batch of points
+    def logp_dlogp(self, q, glm_path=_capi.B2_GLM_AUTO):
+        """q: [n, D] host array or device tensor -> (logp [n] float64, grad [n, D]) device tensors."""
+        torch = self.torch
+        qd = torch.as_tensor(q, device=self.dev).to(self.t_dtype).contiguous()
+        if qd.ndim != 2 or qd.shape[1] != self.D:
+            raise ValueError("Invalid shape for array. Must be (n, %d) but is %s." % (self.D, tuple(qd.shape)))
+        n = qd.shape[0]
+        if n > self.n_chains:
+            raise ValueError("at most n_chains=%d points per call" % self.n_chains)
+        logp = torch.empty(n, dtype=torch.float64, device=self.dev)
+        grad = torch.empty_like(qd)
+        _capi.check(self.lib.b2_logp_dlogp(self.handle, qd.data_ptr(), n, logp.data_ptr(), grad.data_ptr(),
+                                           int(glm_path), self._stream()), self.lib)
+        return logp, grad
+
+    # -- sampling.py:410-413, 883-884, 1915-1929 + base_hmc.py:93-103
+    def set_state(self, q0, seeds, step_size0, mass_mean, mass_var, mass_weight, adaptation_window=101):
+        torch = self.torch
+        q0 = np.asarray(q0, dtype=self.np_dtype).reshape(self.n_chains, self.D)
+        self._q0 = torch.as_tensor(np.ascontiguousarray(q0), device=self.dev)
+        self._seeds = torch.as_tensor(np.asarray(seeds, dtype=np.uint64).view(np.int64).copy(), device=self.dev)
+        self._mm = torch.as_tensor(np.ascontiguousarray(mass_mean, dtype="f8"), device=self.dev)
+        self._mv = torch.as_tensor(np.ascontiguousarray(mass_var, dtype="f8"), device=self.dev)
+        if self._mm.numel() != self.D or self._mv.numel() != self.D:
+            raise ValueError("mass mean/var must have %d elements" % self.D)
+        _capi.check(self.lib.b2_set_state(self.handle, self._q0.data_ptr(), self._seeds.data_ptr(),
+                                          float(step_size0), self._mm.data_ptr(), self._mv.data_ptr(),
+                                          float(mass_weight), int(adaptation_window), self._stream()), self.lib)
+        self.iter_done = 0
+
+    def set_position(self, q):
+        q = np.asarray(q, dtype=self.np_dtype).reshape(self.n_chains, self.D)
+        t = self.torch.as_tensor(np.ascontiguousarray(q), device=self.dev)
+        _capi.check(self.lib.b2_set_position(self.handle, t.data_ptr(), self._stream()), self.lib)
+        self.torch.cuda.synchronize(self.dev)
+
+    # -- the draw loop for all chains (sampling.py:914-936)
+    def run(self, kind, n_iters, tune_until, opts, trace_q=True):
+        """Runs `n_iters` transitions; returns {'q': [n, C, D], stat: [n, C]} device tensors."""
+        torch = self.torch
+        names = _NUTS_STATS if kind == _capi.B2_NUTS else _HMC_STATS
+        out, tr = {}, _capi.TraceOut()
+        if trace_q:
+            out["q"] = torch.empty((n_iters, self.n_chains, self.D), dtype=self.t_dtype, device=self.dev)
+            tr.d_q = out["q"].data_ptr()
+        for name, code in names.items():
+            t = torch.zeros((n_iters, self.n_chains), device=self.dev,
+                            dtype={"f8": torch.float64, "i4": torch.int32, "u1": torch.uint8}[code])
+            out[name] = t
+            setattr(tr, "d_" + name, t.data_ptr())
+        o = _capi.SamplerOpts(kind=kind, n_iters=int(n_iters), tune_until=int(tune_until), **opts)
+        _capi.check(self.lib.b2_sample_run(self.handle, C.byref(o), C.byref(tr), self._stream()), self.lib)
+        self.iter_done += int(n_iters)
+        return out
+
+    def reports(self):
+        arr = (_capi.ChainReport * self.n_chains)()
+        _capi.check(self.lib.b2_get_chain_reports(self.handle, arr), self.lib)
+        return list(arr)
+
+    def mass_var(self):
+        out = np.empty((self.n_chains, self.D))
+        _capi.check(self.lib.b2_get_mass_var(self.handle, out.ctypes.data), self.lib)
+        return out
+
+    def position(self):
+        out = np.empty((self.n_chains, self.D))
+        _capi.check(self.lib.b2_get_position(self.handle, out.ctypes.data), self.lib)
+        return out
+
+    def kernel_launches(self):
+        return int(self.lib.b2_kernel_launches(self.handle))
