@@ -149,6 +149,12 @@ int b2_get_position(b2_engine* e, double* host_out /* [C, D] */);
 /* how many of this library's kernels were launched by the engine so far */
 int64_t b2_kernel_launches(b2_engine* e);
 
+/* live CUDA-event timing of the chain-batched likelihood launches in lock-step mode (the
+ * reference's analogue is theano profiling, model.py:668-671): total ms and launch count
+ * since b2_set_profiling(e, 1). */
+int b2_set_profiling(b2_engine* e, int32_t on);
+int b2_get_profile(b2_engine* e, double* likelihood_ms, int64_t* likelihood_launches);
+
 #ifdef __cplusplus
 }
 #endif

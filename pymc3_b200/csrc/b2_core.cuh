@@ -29,7 +29,8 @@
 
 #define B2_MAX_LEVELS 12          // stack buffers; max_treedepth <= 12
 
-enum { B2_PHASE_INIT = 0, B2_PHASE_TREE = 1, B2_PHASE_HMC = 2, B2_PHASE_DONE = 3, B2_PHASE_FAILED = 4 };
+enum { B2_PHASE_INIT = 0, B2_PHASE_TREE = 1, B2_PHASE_HMC = 2, B2_PHASE_DONE = 3, B2_PHASE_FAILED = 4,
+       B2_PHASE_RESUME = 5 };   // RESUME: a finished chain asked to continue (next b2_sample_run call)
 enum { B2_KIND_NUTS = 0, B2_KIND_HMC = 1 };
 enum { B2_FAIL_NONE = 0, B2_FAIL_BAD_INITIAL_ENERGY = 1 };
 
@@ -558,6 +559,9 @@ B2_HD bool b2_advance(const G& g, const B2View<T>& w, int c, B2ChainState& s, do
         s.cur_logp = logp_new;
         s.n_grad += 1;
         b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.V(B2_V_GE1, c));
+        if (s.iter >= w.iter_end) s.phase = B2_PHASE_DONE;
+        else act = B2_ACT_BEGIN_TRANSITION;
+    } else if (s.phase == B2_PHASE_RESUME) {              // continue from the last draw: no new gradient needed
         if (s.iter >= w.iter_end) s.phase = B2_PHASE_DONE;
         else act = B2_ACT_BEGIN_TRANSITION;
     } else if (s.phase == B2_PHASE_TREE) {

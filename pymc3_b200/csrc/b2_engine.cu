@@ -74,25 +74,32 @@ __global__ void __launch_bounds__(B2_BLOCK_NT) k_logp_block(B2ModelData m, const
     logp_group_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, m, qA, qB, gA, gB, ld, st, blockIdx.x, logp);
 }
 
+// resume_only: the launch that re-activates finished chains at the start of a continuation run
 template <typename T>
-__global__ void k_advance_warp(B2View<T> w) {
+__global__ void k_advance_warp(B2View<T> w, int resume_only) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= w.C) return;
     B2WarpGroup g;
     B2ChainState s = w.st[c];
-    if (!b2_needs_grad(s.phase)) return;
+    if (resume_only) {
+        if (s.phase != B2_PHASE_DONE) return;
+        s.phase = B2_PHASE_RESUME;
+    } else if (!b2_needs_grad(s.phase)) return;
     b2_advance<T, B2WarpGroup>(g, w, c, s, w.logp_eval[c]);
     if (g.lane() == 0) w.st[c] = s;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w) {
+__global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w, int resume_only) {
     __shared__ double red[8 * (B2_BLOCK_NT / 32)];
     B2BlockGroup<B2_BLOCK_NT> g;
     g.red = red;
     const int c = blockIdx.x;
     B2ChainState s = w.st[c];
-    if (!b2_needs_grad(s.phase)) return;
+    if (resume_only) {
+        if (s.phase != B2_PHASE_DONE) return;
+        s.phase = B2_PHASE_RESUME;
+    } else if (!b2_needs_grad(s.phase)) return;
     b2_advance<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, c, s, w.logp_eval[c]);
     if (g.lane() == 0) w.st[c] = s;
 }
@@ -100,6 +107,10 @@ __global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w) {
 template <typename T, typename G>
 __device__ __forceinline__ void persistent_body(const G& g, const B2View<T>& w, const B2ModelData& m, int c) {
     B2ChainState s = w.st[c];
+    if (s.phase == B2_PHASE_DONE && s.iter < w.iter_end) {   // continuation run
+        s.phase = B2_PHASE_RESUME;
+        b2_advance<T, G>(g, w, c, s, 0.0);
+    }
     bool active = b2_needs_grad(s.phase);
     while (active) {
         const T* q = w.V(B2_V_QE0 + s.sel, c);
@@ -275,6 +286,7 @@ extern "C" int b2_engine_destroy(b2_engine* e) {
     cudaFree(e->vec); cudaFree(e->wv_mean); cudaFree(e->wv_m2); cudaFree(e->st); cudaFree(e->logp_eval);
     cudaFree(e->glm_scratch); cudaFree(e->d_active); cudaFree(e->glm_ws); cudaFree(e->hier_ws);
     cudaFreeHost(e->h_active);
+    if (e->ev[0]) for (int i = 0; i < 64; ++i) cudaEventDestroy(e->ev[i]);
     delete e;
     return 0;
 }
@@ -390,12 +402,19 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         const T* qA = w.V(B2_V_QE0, 0); const T* qB = w.V(B2_V_QE1, 0);
         T* gA = w.V(B2_V_GE0, 0); T* gB = w.V(B2_V_GE1, 0);
         const int batch = 32;
+        if (e->iter_done > 0) {                       // re-activate chains that finished the previous call
+            if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 1);
+            else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 1);
+            e->launches += 1;
+        }
         for (;;) {
             for (int b = 0; b < batch; ++b) {
+                if (e->profile) cudaEventRecord(e->ev[2 * b], s);
                 int rc = launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
                 if (rc) return rc;
-                if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w);
-                else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w);
+                if (e->profile) cudaEventRecord(e->ev[2 * b + 1], s);
+                if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 0);
+                else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 0);
                 e->launches += 1;
             }
             B2_CUDA_OK(cudaMemsetAsync(e->d_active, 0, sizeof(int), s));
@@ -403,6 +422,12 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
             e->launches += 1;
             B2_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
             B2_CUDA_OK(cudaStreamSynchronize(s));
+            if (e->profile) {
+                for (int b = 0; b < batch; ++b) {
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, e->ev[2 * b], e->ev[2 * b + 1]) == cudaSuccess) { e->like_ms += ms; e->like_n += 1; }
+                }
+            }
             if (*e->h_active == 0) break;
         }
         B2_CUDA_OK(cudaGetLastError());
@@ -462,3 +487,19 @@ extern "C" int b2_get_position(b2_engine* e, double* out) {
 }
 
 extern "C" int64_t b2_kernel_launches(b2_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int b2_set_profiling(b2_engine* e, int32_t on) {
+    if (!e) { b2_set_error("b2_set_profiling: null engine"); return -1; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    if (on && !e->ev[0])
+        for (int i = 0; i < 64; ++i) B2_CUDA_OK(cudaEventCreate(&e->ev[i]));
+    e->profile = on ? 1 : 0;
+    e->like_ms = 0.0; e->like_n = 0;
+    return 0;
+}
+
+extern "C" int b2_get_profile(b2_engine* e, double* likelihood_ms, int64_t* likelihood_launches) {
+    if (!e || !likelihood_ms || !likelihood_launches) { b2_set_error("b2_get_profile: null argument"); return -1; }
+    *likelihood_ms = e->like_ms; *likelihood_launches = e->like_n;
+    return 0;
+}

@@ -26,6 +26,11 @@ struct b2_engine {
     bool state_set;
     int64_t launches;
     int sm_count;
+    // optional live timing of the likelihood launches (bench.py roofline)
+    int profile;
+    double like_ms;
+    int64_t like_n;
+    cudaEvent_t ev[64];
 };
 
 void b2_set_error(const std::string& msg);

@@ -141,5 +141,14 @@ class Engine:
         _capi.check(self.lib.b2_get_position(self.handle, out.ctypes.data), self.lib)
         return out
 
+    def set_profiling(self, on=True):
+        _capi.check(self.lib.b2_set_profiling(self.handle, int(bool(on))), self.lib)
+
+    def profile(self):
+        """(total ms, launches) of the chain-batched likelihood kernel since set_profiling(True)."""
+        ms, n = C.c_double(), C.c_int64()
+        _capi.check(self.lib.b2_get_profile(self.handle, C.byref(ms), C.byref(n)), self.lib)
+        return ms.value, n.value
+
     def kernel_launches(self):
         return int(self.lib.b2_kernel_launches(self.handle))

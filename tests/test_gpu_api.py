@@ -1,0 +1,212 @@
+"""The reference-facing Python surface on a real GPU.  These read like the reference's own tests:
+pymc3/tests/test_step.py:943-1008, test_hmc.py:49-66, test_sampling.py:41-236,
+test_ndarray_backend.py, sampler_fixtures.py:24-56,150-176."""
+import numpy as np
+import pytest
+
+import pymc3_b200 as pm
+from pymc3_b200.exceptions import SamplingError
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def schools_trace():
+    with pm.EightSchoolsNCP(mu_sd=5.0, tau_beta=5.0) as model:
+        trace = pm.sample(500, tune=500, chains=8, random_seed=3, step=pm.NUTS(dtype="float64"))
+    return model, trace
+
+
+def test_sampler_stats_names_shapes_and_model_logp(schools_trace):
+    """test_step.py:980-1008."""
+    model, trace = schools_trace
+    expected = {"depth", "diverging", "energy", "energy_error", "model_logp", "max_energy_error",
+                "mean_tree_accept", "step_size", "step_size_bar", "tree_size", "tune"}
+    assert trace.stat_names == expected
+    for name in expected:
+        assert trace.get_sampler_stats(name, chains=0).shape == (500,)
+    assert trace.get_sampler_stats("tree_depth").shape == (8 * 500,)
+    f = model.logp_dlogp_function(dtype="float64")
+    model_logp = trace.get_sampler_stats("model_logp", chains=2)
+    for i in (0, 17, 499):
+        q = model.dict_to_array({k: v for k, v in trace.point(i, chain=2).items() if k in model.free_RVs})
+        assert abs(float(f(q)[0]) - model_logp[i]) < 1e-8 * abs(model_logp[i])
+
+
+def test_trace_selection_api(schools_trace):
+    model, trace = schools_trace
+    assert trace.nchains == 8 and len(trace) == 500
+    assert set(trace.varnames) == {"eta", "mu", "tau_log__", "tau"}
+    assert trace["eta"].shape == (4000, 8)
+    assert trace.get_values("mu", combine=False)[3].shape == (500,)
+    assert trace.get_values("mu", burn=100, thin=2, chains=[0, 1]).shape == (400,)
+    assert np.allclose(trace["tau"], np.exp(trace["tau_log__"]))
+    assert len(trace[100:]) == 400 and len(trace[::5]) == 100
+    assert trace["mu", 100::2].shape == (8 * 200,)
+    assert set(trace.point(3).keys()) == set(trace.varnames)
+    assert trace.report.n_tune == 500 and trace.report.n_draws == 500 and trace.report.t_sampling > 0
+    assert not trace.get_sampler_stats("tune").any()
+
+
+def test_posterior_matches_published_table(schools_trace):
+    """SURVEY section 6 (Diagnosing_biased_Inference_with_Divergences.ipynb:1566-1575), MCSE-based z < 4."""
+    model, trace = schools_trace
+    pub = {"mu": (4.46, 3.31), "tau": (3.59, 3.23)}
+    for name, (mean, sd) in pub.items():
+        draws = np.stack(trace.get_values(name, combine=False))
+        mcse = pm.stats.mcse_mean(draws)
+        assert abs(draws.mean() - mean) < 4 * mcse + 0.15          # 0.15: the table's own MC error
+        assert abs(draws.std() - sd) < 0.5
+    acc = trace.get_sampler_stats("mean_tree_accept")
+    assert abs(acc.mean() - 0.8) < 0.08                             # sampler_fixtures.py:174-176
+    assert float(np.max(pm.rhat(np.stack(trace.get_values("mu", combine=False))))) < 1.05
+
+
+def test_discard_tuned_samples_and_lengths():
+    """test_sampling.py:138-147."""
+    with pm.StdNormal(3):
+        t1 = pm.sample(50, tune=30, chains=2, random_seed=1, discard_tuned_samples=True,
+                       compute_convergence_checks=False)
+        t2 = pm.sample(50, tune=30, chains=2, random_seed=1, discard_tuned_samples=False,
+                       compute_convergence_checks=False)
+    assert len(t1) == 50 and len(t2) == 80
+    assert t2.get_sampler_stats("tune", chains=0)[:30].all() and not t2.get_sampler_stats("tune", chains=0)[30:].any()
+    assert np.array_equal(t1["x"], t2[30:]["x"])                    # same seeds -> same chains
+
+
+def test_seeds_reproduce_and_differ():
+    """test_sampling.py:46-73."""
+    with pm.StdNormal(2):
+        a = pm.sample(20, tune=20, chains=2, random_seed=7, compute_convergence_checks=False)
+        b = pm.sample(20, tune=20, chains=2, random_seed=7, compute_convergence_checks=False)
+        c = pm.sample(20, tune=20, chains=2, random_seed=8, compute_convergence_checks=False)
+        d = pm.sample(20, tune=20, chains=2, random_seed=[11, 12], compute_convergence_checks=False)
+    assert np.array_equal(a["x"], b["x"])
+    assert not np.array_equal(a["x"], c["x"])
+    assert d.nchains == 2
+
+
+def test_bad_arguments():
+    """test_sampling.py:99-111, 175-192."""
+    with pm.StdNormal(2) as model:
+        with pytest.raises(ValueError):
+            pm.sample(10, tune=5, chains=1, step=pm.NUTS(), foo=1)
+        with pytest.raises(ValueError):
+            pm.NUTS(foo=1)
+        with pytest.raises(ValueError):
+            pm.sample(10, tune=5, chains=2, start={"x": np.zeros(5)})
+        with pytest.raises(TypeError):
+            pm.sample(10, tune=5, chains=2, random_seed=1.5)
+        with pytest.raises(ValueError):
+            pm.NUTS(scaling=np.ones(2), potential=pm.QuadPotentialDiag(np.ones(2)))
+
+
+def test_bad_initial_energy_raises_sampling_error():
+    """test_hmc.py:59-66, test_step.py:943-956."""
+    with pm.StdNormal(2):
+        with pytest.raises(SamplingError) as err:
+            pm.sample(10, tune=5, chains=2, start={"x": np.array([np.inf, 0.0])}, step=pm.NUTS(),
+                      compute_convergence_checks=False)
+        assert "Bad initial energy" in str(err.value)
+
+
+def test_tuning_reset_step_size_constant_after_tune():
+    """test_hmc.py:49-57."""
+    with pm.StdNormal(4, sigma=[1.0, 2.0, 0.5, 3.0]):
+        step = pm.NUTS()
+        trace = pm.sample(100, tune=200, chains=2, step=step, discard_tuned_samples=False, random_seed=2,
+                          compute_convergence_checks=False)
+    assert step.tune is False
+    ss = trace.get_sampler_stats("step_size", chains=0)
+    assert np.all(ss[200:] == ss[200]) and len(np.unique(ss[:200])) > 50
+    assert np.allclose(step.potential._var, [1.0, 4.0, 0.25, 9.0], rtol=0.6)
+
+
+def test_divergences_are_reported():
+    """test_step.py:958-978: a funnel-like posterior sampled with a too-large fixed step."""
+    with pm.EightSchoolsNCP(tau_beta=25.0):
+        step = pm.NUTS(adapt_step_size=False, step_scale=6.0)
+        trace = pm.sample(200, tune=0, chains=2, step=step, random_seed=5, compute_convergence_checks=False)
+    assert trace.get_sampler_stats("diverging").any()
+    msgs = [w.message for w in trace.report._warnings]
+    assert any("divergence" in m.lower() for m in msgs)
+    assert not trace.report.ok
+    with pytest.raises(ValueError):
+        trace.report.raise_ok()
+
+
+def test_step_interface_single_chain_loop():
+    """step.step(point) one draw at a time (sampling.py:914-936) + iter_sample (test_sampling.py:113)."""
+    with pm.StdNormal(3) as model:
+        step = pm.NUTS(dtype="float64")
+        np.random.seed(4)
+        point = model.test_point
+        xs = []
+        for i in range(60):
+            if i == 40:
+                step.stop_tuning()
+            point, stats = step.step(point)
+            assert set(stats[0]) == set(step.stats_dtypes[0])
+            assert stats[0]["tune"] == (i < 40)
+            xs.append(point["x"])
+        assert np.std(np.array(xs)) > 0.3
+        traces = list(pm.iter_sample(10, pm.NUTS(), tune=5, random_seed=3))
+        assert len(traces) == 10 and len(traces[-1]) == 10 and len(traces[3]) == 4
+
+
+def test_hamiltonian_mc_runs_with_reference_stats():
+    with pm.StdNormal(5, sigma=np.arange(1.0, 6.0)):
+        trace = pm.sample(400, tune=400, chains=4, step=pm.HamiltonianMC(), random_seed=9,
+                          compute_convergence_checks=False)
+    assert trace.stat_names == {"step_size", "n_steps", "tune", "step_size_bar", "accept", "diverging",
+                                "energy_error", "energy", "path_length", "accepted", "model_logp"}
+    assert np.allclose(trace["x"].std(axis=0), np.arange(1.0, 6.0), rtol=0.25)
+    assert abs(trace.get_sampler_stats("accept").mean() - 0.65) < 0.15
+
+
+def test_scaling_argument_and_guess_scaling():
+    """test_step.py:505-527 builds NUTS(scaling=model.test_point): diag Hessian -> QuadPotentialDiag."""
+    with pm.StdNormal(3, sigma=[1.0, 2.0, 0.5]) as model:
+        step = pm.NUTS(scaling=model.test_point)
+        assert isinstance(step.potential, pm.QuadPotentialDiag)
+        assert np.allclose(step.potential.v, [1.0, 4.0, 0.25], rtol=1e-3)
+        trace = pm.sample(300, tune=300, chains=2, step=step, random_seed=1, compute_convergence_checks=False)
+    assert np.allclose(trace["x"].std(axis=0), [1.0, 2.0, 0.5], rtol=0.25)
+
+
+def test_value_grad_function_interface():
+    """test_model.py:244-318 (interface part) + developer_guide dict<->array round trip."""
+    model = pm.EightSchoolsNCP()
+    f = model.logp_dlogp_function()
+    assert f.size == 10 and f.dtype == np.float64
+    with pytest.raises(TypeError):
+        model.logp_dlogp_function(dtype="int32")
+    arr = np.arange(10, dtype="f8") / 10
+    point = f.array_to_dict(arr)
+    assert np.allclose(f.dict_to_array(point), arr)
+    logp, grad = f(arr)
+    out = np.empty(10)
+    logp2 = f(arr, grad_out=out)
+    assert logp == logp2 and np.array_equal(grad, out)
+    with pytest.raises(ValueError):
+        f(np.zeros(3))
+
+
+def test_multi_device_chain_sharding_is_device_count_invariant():
+    import torch
+    n = torch.cuda.device_count()
+    devices = list(range(min(n, 2))) * (2 if n < 2 else 1)         # 1 GPU: two engines on the same device
+    with pm.StdNormal(3):
+        a = pm.sample(30, tune=30, chains=6, random_seed=5, compute_convergence_checks=False)
+        b = pm.sample(30, tune=30, chains=6, random_seed=5, devices=devices, compute_convergence_checks=False)
+    assert np.array_equal(a["x"], b["x"])
+
+
+def test_save_load_trace_roundtrip(tmp_path, schools_trace):
+    """test_ndarray_backend.py:203-280."""
+    model, trace = schools_trace
+    d = pm.save_trace(trace[:50], str(tmp_path / "t"), overwrite=True)
+    back = pm.load_trace(d, model=model)
+    assert back.nchains == 8 and len(back) == 50
+    assert np.array_equal(back["mu"], trace[:50]["mu"])
+    assert np.array_equal(back.get_sampler_stats("depth"), trace[:50].get_sampler_stats("depth"))

@@ -1,0 +1,244 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI, against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): logp/dlogp within 1e-6 relative in the fp64 check build,
+1e-4 in the fp32 production build; tree-building decisions reproducible for a fixed RNG stream.
+"""
+import numpy as np
+import pytest
+
+from oracle.hmc_cpu import CpuHMC, CpuNUTS, run_chain
+from oracle.potentials import DiagAdaptPotential
+from oracle.rng import PhiloxRNG
+from pymc3_b200 import _capi
+from tests import models_util
+
+pytestmark = pytest.mark.gpu
+
+NUTS_OPTS = dict(max_treedepth=10, early_max_treedepth=8, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75,
+                 t0=10.0, adapt_step_size=1, adapt_mass=1, path_length=2.0, max_steps=1024, hmc_jitter=1,
+                 exec_mode=0, glm_path=0)
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", ["std_normal", "eight_schools", "glm", "hier", "stoch_vol"])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-6), ("float32", 1e-4)])
+def test_logp_dlogp_matches_oracle(name, dtype, tol):
+    model, oracle = models_util.pairs()[name]
+    rng = np.random.default_rng(5)
+    q = rng.normal(size=(16, oracle.ndim)) * 0.4
+    eng = model.engine(16, dtype=dtype)
+    logp, grad = eng.logp_dlogp(q)
+    logp, grad = logp.cpu().numpy(), grad.cpu().numpy().astype("f8")
+    for i in range(len(q)):
+        l0, g0 = oracle(q[i].astype(dtype).astype("f8"))
+        assert abs(logp[i] - l0) <= tol * max(1.0, abs(l0)), (name, i, logp[i], l0)
+        assert _rel(grad[i], g0) <= tol, (name, i)
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-6), ("float32", 1e-4)])
+@pytest.mark.parametrize("path", [_capi.B2_GLM_GROUP, _capi.B2_GLM_SIMT])
+def test_glm_chain_batched_paths(dtype, tol, path):
+    """ragged sizes: N not a multiple of the 64-row tile, chains not a multiple of 64, K odd."""
+    from oracle import densities as od
+    from pymc3_b200 import model as pm
+    X, y = models_util.glm_data(1000 + 37, 13, seed=7)
+    model, oracle = pm.LogisticGLM(X, y), od.LogisticGLM(X, y)
+    rng = np.random.default_rng(6)
+    q = rng.normal(size=(70, oracle.ndim)) * 0.5
+    eng = model.engine(70, dtype=dtype)
+    logp, grad = eng.logp_dlogp(q, glm_path=path)
+    logp, grad = logp.cpu().numpy(), grad.cpu().numpy().astype("f8")
+    for i in range(len(q)):
+        l0, g0 = oracle(q[i].astype(dtype).astype("f8"))
+        assert abs(logp[i] - l0) <= tol * abs(l0)
+        assert _rel(grad[i], g0) <= tol
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-6), ("float32", 2e-4)])
+def test_hier_chain_batched_kernel(dtype, tol):
+    from oracle import densities as od
+    from pymc3_b200 import model as pm
+    idx, floor, y = models_util.hier_data(40000 + 123, 85, seed=2)
+    model, oracle = pm.HierLinearNCP(idx, floor, y, 85), od.HierLinearNCP(idx, floor, y, 85)
+    rng = np.random.default_rng(8)
+    q = rng.normal(size=(130, oracle.ndim)) * 0.3
+    eng = model.engine(130, dtype=dtype)       # 130 * 40123 >= 2^22 -> chain-batched slab kernel
+    logp, grad = eng.logp_dlogp(q)
+    logp, grad = logp.cpu().numpy(), grad.cpu().numpy().astype("f8")
+    for i in range(0, len(q), 7):
+        l0, g0 = oracle(q[i].astype(dtype).astype("f8"))
+        assert abs(logp[i] - l0) <= tol * abs(l0)
+        assert _rel(grad[i], g0) <= tol
+    eng.close()
+
+
+def _run_engine(model, q0, seeds, n, tune, kind, dtype, exec_mode, step0=None, **over):
+    eng = model.engine(len(q0), dtype=dtype)
+    D = eng.D
+    eng.set_state(q0, seeds, step0 or 0.25 / D ** 0.25, np.zeros(D), np.ones(D), 10.0)
+    opts = dict(NUTS_OPTS)
+    if kind == _capi.B2_HMC:
+        opts["target_accept"] = 0.65
+    opts.update(over)
+    opts["exec_mode"] = exec_mode
+    out = eng.run(kind, n, tune, opts)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    out["reports"] = eng.reports()
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("name", ["std_normal", "eight_schools", "glm", "hier", "stoch_vol"])
+@pytest.mark.parametrize("exec_mode", [_capi.B2_EXEC_PERSISTENT, _capi.B2_EXEC_LOCKSTEP])
+def test_nuts_decisions_match_recursive_oracle(name, exec_mode):
+    """fp64, fixed step size: 150 transitions (100 tuning with mass adaptation) draw for draw."""
+    model, oracle = models_util.pairs()[name]
+    D = oracle.ndim
+    rng = np.random.default_rng(1)
+    C = 3
+    q0 = rng.uniform(-1, 1, size=(C, D))
+    seeds = [11, 2 ** 40 + 5, 123456789]
+    # stochastic volatility trajectories are chaotic enough to amplify summation-order
+    # round-off past 1e-7 after ~100 draws (same on the CPU, see tests/test_hostsim.py): shorter run
+    n, tune = (60, 40) if name == "stoch_vol" else (150, 110)
+    step0 = 0.02 if name == "hier" else None        # the default start step diverges on this posterior
+    out = _run_engine(model, q0, seeds, n, tune, _capi.B2_NUTS, "float64", exec_mode, step0=step0,
+                      adapt_step_size=0)
+    for c in range(C):
+        s = CpuNUTS(oracle, D, DiagAdaptPotential(D, np.zeros(D), np.ones(D), 10), PhiloxRNG(seeds[c]),
+                    adapt_step_size=False)
+        if step0:
+            s.adapter.log_step = s.adapter.log_bar = np.log(step0)
+        qs, st = run_chain(s, q0[c], n, tune)
+        assert (st["depth"] == out["depth"][:, c]).all()
+        assert (st["tree_size"] == out["tree_size"][:, c]).all()
+        assert (st["diverging"] == out["diverging"][:, c].astype(bool)).all()
+        assert np.abs(qs - out["q"][:, c]).max() < 1e-7
+        assert np.abs(st["energy"] - out["energy"][:, c]).max() < 1e-6
+        assert np.abs(st["mean_tree_accept"] - out["mean_tree_accept"][:, c]).max() < 1e-7
+        assert out["reports"][c].phase == _capi.PHASE_DONE
+        assert out["reports"][c].n_grad == st["tree_size"].sum() + 1
+
+
+def test_nuts_with_dual_averaging_matches_oracle_early():
+    """with step-size adaptation the tuning dynamics amplify round-off, so compare the first draws"""
+    model, oracle = models_util.pairs()["eight_schools"]
+    D = oracle.ndim
+    q0 = np.random.default_rng(2).uniform(-1, 1, size=(2, D))
+    seeds = [7, 8]
+    out = _run_engine(model, q0, seeds, 30, 30, _capi.B2_NUTS, "float64", _capi.B2_EXEC_AUTO)
+    for c in range(2):
+        s = CpuNUTS(oracle, D, DiagAdaptPotential(D, np.zeros(D), np.ones(D), 10), PhiloxRNG(seeds[c]))
+        qs, st = run_chain(s, q0[c], 30, 30)
+        assert (st["depth"][:20] == out["depth"][:20, c]).all()
+        assert np.abs(qs[:15] - out["q"][:15, c]).max() < 1e-6
+        assert np.abs(st["step_size"][:15] - out["step_size"][:15, c]).max() < 1e-6
+        assert np.abs(st["step_size_bar"][:15] - out["step_size_bar"][:15, c]).max() < 1e-6
+
+
+@pytest.mark.parametrize("exec_mode", [_capi.B2_EXEC_PERSISTENT, _capi.B2_EXEC_LOCKSTEP])
+def test_hmc_matches_oracle(exec_mode):
+    model, oracle = models_util.pairs()["std_normal"]
+    D = oracle.ndim
+    q0 = np.random.default_rng(3).uniform(-1, 1, size=(2, D))
+    seeds = [21, 22]
+    out = _run_engine(model, q0, seeds, 200, 150, _capi.B2_HMC, "float64", exec_mode, adapt_step_size=0)
+    for c in range(2):
+        s = CpuHMC(oracle, D, DiagAdaptPotential(D, np.zeros(D), np.ones(D), 10), PhiloxRNG(seeds[c]),
+                   adapt_step_size=False)
+        qs, st = run_chain(s, q0[c], 200, 150)
+        assert (st["n_steps"] == out["n_steps"][:, c]).all()
+        assert (st["accepted"] == out["accepted"][:, c].astype(bool)).all()
+        assert np.abs(qs - out["q"][:, c]).max() < 1e-6
+        assert np.abs(st["accept"] - out["accept"][:, c]).max() < 1e-6
+
+
+def test_fp32_production_build_runs_and_is_sane():
+    """priors of the reference's published eight-schools table: mu~N(0,5),
+    tau~HalfCauchy(5) -> posterior mu 4.46 (sd 3.31), tau 3.59 (sd 3.23)."""
+    from pymc3_b200 import model as pm
+    model = pm.EightSchoolsNCP(mu_sd=5.0, tau_beta=5.0)
+    D = 10
+    C = 64
+    rng = np.random.default_rng(4)
+    q0 = rng.uniform(-1, 1, size=(C, D))
+    out = _run_engine(model, q0, np.arange(C) + 100, 600, 300, _capi.B2_NUTS, "float32", _capi.B2_EXEC_AUTO)
+    acc = out["mean_tree_accept"][300:].mean()
+    assert 0.7 < acc < 0.95
+    mu = out["q"][300:, :, 8]
+    tau = np.exp(out["q"][300:, :, 9])
+    assert abs(mu.mean() - 4.46) < 0.35 and abs(mu.std() - 3.31) < 0.35
+    assert abs(tau.mean() - 3.59) < 0.4
+    assert out["tune"][:300].all() and not out["tune"][300:].any()
+
+
+def test_bad_initial_energy_is_reported():
+    from pymc3_b200 import model as pm
+    model = pm.StdNormal(3)
+    eng = model.engine(2, dtype="float64")
+    q0 = np.array([[0.0, 0.0, 0.0], [np.inf, 0.0, 0.0]])
+    eng.set_state(q0, [1, 2], 0.1, np.zeros(3), np.ones(3), 10.0)
+    eng.run(_capi.B2_NUTS, 5, 5, dict(NUTS_OPTS))
+    rep = eng.reports()
+    assert rep[0].phase == _capi.PHASE_DONE
+    assert rep[1].phase == _capi.PHASE_FAILED and rep[1].fail_code == _capi.FAIL_BAD_INITIAL_ENERGY
+    eng.close()
+
+
+@pytest.mark.parametrize("exec_mode", [_capi.B2_EXEC_PERSISTENT, _capi.B2_EXEC_LOCKSTEP])
+def test_block_per_chain_group_on_full_stochastic_volatility(exec_mode):
+    """D = 2907 > 1024 -> a whole block owns a chain (config C4's mapping)."""
+    from oracle import densities as od
+    from pymc3_b200 import model as pm
+    model, oracle = pm.StochVol(), od.StochVol(pm.sp500_log_returns())
+    D = oracle.ndim
+    assert D == 2907
+    rng = np.random.default_rng(9)
+    q0 = rng.uniform(-1, 1, size=(2, D)) * 0.1
+    q0[:, 0] = -3.0
+    q0[:, -1] = 2.0
+    eng = model.engine(2, dtype="float64")
+    logp, grad = eng.logp_dlogp(q0)
+    for c in range(2):
+        l0, g0 = oracle(q0[c])
+        assert abs(logp.cpu().numpy()[c] - l0) <= 1e-9 * abs(l0)
+        assert _rel(grad.cpu().numpy()[c], g0) <= 1e-9
+    eng.close()
+    seeds = [31, 32]
+    n = 12
+    out = _run_engine(model, q0, seeds, n, n, _capi.B2_NUTS, "float64", exec_mode, adapt_step_size=0,
+                      early_max_treedepth=5)
+    for c in range(2):
+        s = CpuNUTS(oracle, D, DiagAdaptPotential(D, np.zeros(D), np.ones(D), 10), PhiloxRNG(seeds[c]),
+                    adapt_step_size=False, early_max_treedepth=5)
+        qs, st = run_chain(s, q0[c], n, n)
+        assert (st["depth"] == out["depth"][:, c]).all()
+        assert (st["tree_size"] == out["tree_size"][:, c]).all()
+        assert np.abs(qs - out["q"][:, c]).max() < 1e-7
+
+
+@pytest.mark.parametrize("exec_mode", [_capi.B2_EXEC_PERSISTENT, _capi.B2_EXEC_LOCKSTEP])
+def test_chunked_runs_continue_the_same_chains(exec_mode):
+    """b2_sample_run called 3 x 20 iterations == one call of 60 (device state persists)."""
+    model, oracle = models_util.pairs()["eight_schools"]
+    D = oracle.ndim
+    q0 = np.random.default_rng(12).uniform(-1, 1, size=(5, D))
+    seeds = np.arange(5) + 40
+    one = _run_engine(model, q0, seeds, 60, 40, _capi.B2_NUTS, "float64", exec_mode)
+    eng = model.engine(5, dtype="float64")
+    eng.set_state(q0, seeds, 0.25 / D ** 0.25, np.zeros(D), np.ones(D), 10.0)
+    opts = dict(NUTS_OPTS)
+    opts["exec_mode"] = exec_mode
+    parts = [eng.run(_capi.B2_NUTS, 20, 40, opts) for _ in range(3)]
+    q = np.concatenate([p["q"].cpu().numpy() for p in parts])
+    depth = np.concatenate([p["depth"].cpu().numpy() for p in parts])
+    tune = np.concatenate([p["tune"].cpu().numpy() for p in parts])
+    assert np.array_equal(q, one["q"]) and np.array_equal(depth, one["depth"])
+    assert tune[:40].all() and not tune[40:].any()
+    assert all(r.iter == 60 for r in eng.reports())
+    eng.close()
