@@ -284,6 +284,7 @@ extern "C" int b2_engine_destroy(b2_engine* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
     cudaFree(e->vec); cudaFree(e->wv_mean); cudaFree(e->wv_m2); cudaFree(e->st); cudaFree(e->logp_eval);
+    b2_glm_tc_release(e);
     cudaFree(e->glm_scratch); cudaFree(e->d_active); cudaFree(e->glm_ws); cudaFree(e->hier_ws);
     cudaFreeHost(e->h_active);
     if (e->ev[0]) for (int i = 0; i < 64; ++i) cudaEventDestroy(e->ev[i]);

@@ -20,6 +20,7 @@ struct b2_engine {
     int* h_active;             // pinned host mirror
     void* glm_ws;              // workspace of the chain-batched GLM kernels (b2_glm_*.cu)
     size_t glm_ws_bytes;
+    void* glm_tc;              // state of the tcgen05 GLM path (b2_glm_tc.cu), or null
     void* hier_ws;             // workspace of the chain-batched hierarchical kernel
     size_t hier_ws_bytes;
     int iter_done;             // iterations completed by every chain so far
@@ -51,6 +52,7 @@ int b2_glm_simt_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int
 int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
                      const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);
 bool b2_glm_tc_supported(const b2_engine* e);
+void b2_glm_tc_release(b2_engine* e);
 template <typename T>
 int b2_hier_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
                    const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);

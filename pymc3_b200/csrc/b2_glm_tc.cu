@@ -1,9 +1,453 @@
-// tcgen05 / TMA chain-batched GLM likelihood -- placeholder until the kernel lands.
+// Chain-batched Bernoulli-logit GLM likelihood on the 5th-generation tensor cores (sm_100a).
+//
+//   eta[c, i] = sum_k q[c, k] Xa[i, k]                 (Xa = [1 | X], K1 = K + 1 <= 128 columns)
+//   logp_c    = sum_i y_i eta - softplus(eta)          (+ prior, added in the finalize kernel)
+//   grad_c[k] = sum_i (y_i - sigmoid(eta[c, i])) Xa[i, k]
+// (reference: pymc3/glm/linear.py:49-101, glm/families.py:115-119, discrete.py:104,350 evaluated by
+//  the Theano-compiled ValueGradFunction.__call__, model.py:645-666 -- two GEMVs per chain there.)
+//
+// One CTA owns 128 chains (the MMA M dimension) and a contiguous range of 64-observation tiles.
+// Per tile, flash-attention style, with nothing but the X tile crossing HBM/L2:
+//   GEMM1  S[128 chains, 64 obs]   = Q . Xtile^T     tcgen05.mma SS, A = Q (smem), B = Xtile (smem, K-major)
+//   epi    R = y - sigmoid(S), logp += ...           tcgen05.ld -> registers -> bf16 hi/lo -> tcgen05.st (TMEM)
+//   GEMM2  G[128 chains, 128 feat] += R . Xtile      tcgen05.mma TS, A = R (TMEM), B = the SAME smem tile, MN-major
+// fp32-level accuracy from bf16 tensor cores by two-term splits (x = hi + lo, both bf16):
+//   S = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo ,   G = Rhi.Xhi + Rlo.Xhi + Rhi.Xlo      (error ~2^-17 per product)
+// Operands are staged by cp.async.bulk (TMA engine, 1-D bulk copies): X is pre-tiled ONCE at model
+// build into the exact 128B-swizzled shared-memory image the UMMA descriptors expect, so a pipeline
+// stage is one contiguous 33 KB copy and no tensor map is needed.  Accumulators live in TMEM
+// (S double-buffered 2x64 cols, R 2x64 cols, G 128 cols).  Warp roles: 0 = bulk-copy producer,
+// 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..7 = epilogue warpgroup (lane == chain).
+#include <cuda_bf16.h>
+#include <cstring>
 #include "b2_engine.cuh"
-bool b2_glm_tc_supported(const b2_engine* e) { (void)e; return false; }
-int b2_glm_tc_launch(b2_engine* e, const float*, const float*, float*, float*, int, const B2ChainState*, int,
-                     double*, cudaStream_t) {
-    (void)e;
-    b2_set_error("tcgen05 GLM kernel not built");
-    return -6;
+
+#define TC_CHAINS 128                 // MMA M
+#define TC_OBS 64                     // observations per tile (GEMM1 N, GEMM2 K)
+#define TC_KP 128                     // padded feature count (GEMM1 K, GEMM2 N)
+#define TC_STAGES 4
+#define TC_XPART_BYTES (TC_OBS * TC_KP * 2)            // 16384: one of {hi, lo}, two 64-column atoms
+#define TC_STAGE_DATA (2 * TC_XPART_BYTES + TC_OBS * 4) // 33024: Xhi | Xlo | y
+#define TC_STAGE_BYTES 33792                           // padded to a multiple of 1024
+#define TC_QPART_BYTES (TC_CHAINS * TC_KP * 2)         // 32768
+#define TC_Q_BYTES (2 * TC_QPART_BYTES)                // 65536
+#define TC_SMEM_BYTES (1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256)
+#define TC_THREADS 256
+#define TC_TMEM_COLS 512
+#define TC_COL_S 0                    // S[b] at 64 b
+#define TC_COL_P 128                  // P[b] at 128 + 64 b   (hi: 32 cols, lo: 32 cols; 2 bf16 per column)
+#define TC_COL_G 256                  // 128 columns
+
+struct TcWorkspace {
+    unsigned char* xt;       // [n_tiles][TC_STAGE_DATA] pre-swizzled X tiles (+ y)
+    unsigned char* qt;       // [chain_tiles][TC_Q_BYTES] swizzled Q tiles, rewritten every launch
+    float* gpart;            // [splits][c_pad][TC_KP]
+    double* lpart;           // [splits][c_pad]
+    int n_tiles, c_pad, chain_tiles, splits, tiles_per_split, n_pad_rows;
+    int* err;                // device watchdog flag
+};
+
+// byte offset of element (row, col) inside a [rows][64]-bf16 atom with the 128B swizzle
+// (Swizzle<3,4,3>: 16-byte chunk index ^= row % 8) -- the image TMA SWIZZLE_128B would produce.
+__host__ __device__ __forceinline__ int tc_swz(int row, int col) {
+    return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
+}
+
+// ------------------------------------------------------------------------ one-time X tiling
+__global__ void k_glm_tc_prep_x(const float* __restrict__ X, const float* __restrict__ y, int N, int K,
+                                unsigned char* __restrict__ xt, int n_tiles) {
+    const int tile = blockIdx.x;
+    unsigned char* blob = xt + (size_t)tile * TC_STAGE_DATA;
+    for (int idx = threadIdx.x; idx < TC_OBS * TC_KP; idx += blockDim.x) {
+        const int r = idx / TC_KP, c = idx - r * TC_KP;
+        const int row = tile * TC_OBS + r;
+        float v = 0.f;
+        if (row < N) {
+            if (c == 0) v = 1.f;                                   // intercept column
+            else if (c <= K) v = X[(size_t)row * K + (c - 1)];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int off = (c >> 6) * (TC_OBS * 128) + tc_swz(r, c & 63);
+        *reinterpret_cast<__nv_bfloat16*>(blob + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(blob + TC_XPART_BYTES + off) = lo;
+    }
+    for (int r = threadIdx.x; r < TC_OBS; r += blockDim.x) {
+        const int row = tile * TC_OBS + r;
+        reinterpret_cast<float*>(blob + 2 * TC_XPART_BYTES)[r] = row < N ? y[row] : 0.f;
+    }
+}
+
+// ------------------------------------------------------- per-launch split of the positions
+__global__ void k_glm_tc_pack_q(const float* qA, const float* qB, int ld, const B2ChainState* st, int n_chains,
+                                int K1, unsigned char* __restrict__ qt) {
+    const int ctile = blockIdx.x;
+    unsigned char* blob = qt + (size_t)ctile * TC_Q_BYTES;
+    for (int idx = threadIdx.x; idx < TC_CHAINS * TC_KP; idx += blockDim.x) {
+        const int r = idx / TC_KP, c = idx - r * TC_KP;
+        const int chain = ctile * TC_CHAINS + r;
+        float v = 0.f;
+        if (chain < n_chains && c < K1) {
+            int sel = 0;
+            bool live = true;
+            if (st) { live = st[chain].phase <= B2_PHASE_HMC; sel = st[chain].sel; }
+            if (live) v = (sel ? qB : qA)[(size_t)chain * ld + c];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int off = (c >> 6) * (TC_CHAINS * 128) + tc_swz(r, c & 63);
+        *reinterpret_cast<__nv_bfloat16*>(blob + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(blob + TC_QPART_BYTES + off) = lo;
+    }
+}
+
+// ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug becomes an error flag + trap instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int tag) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) {
+            if (err) atomicExch(err, tag);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+#define TC_LD32(taddr, v)                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                  \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                  \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                 \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),       \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+                 : "r"(taddr) : "memory")
+#define TC_ST16(taddr, v)                                                                                   \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                            \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                \
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory")
+
+// instruction descriptors (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16
+#define TC_IDESC_BASE ((1u << 4) | (1u << 7) | (1u << 10))
+#define TC_IDESC_G1 (TC_IDESC_BASE | ((TC_OBS >> 3) << 17) | ((TC_CHAINS >> 4) << 24))               // N=64,  K-major B
+#define TC_IDESC_G2 (TC_IDESC_BASE | (1u << 16) | ((TC_KP >> 3) << 17) | ((TC_CHAINS >> 4) << 24))   // N=128, MN-major B
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* q_s = smem;
+    unsigned char* x_s = smem + TC_Q_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* q_full = bars;                       // 1
+    uint64_t* x_full = bars + 1;                   // TC_STAGES
+    uint64_t* x_empty = x_full + TC_STAGES;        // TC_STAGES
+    uint64_t* s_full = x_empty + TC_STAGES;        // 2
+    uint64_t* s_empty = s_full + 2;                // 2
+    uint64_t* p_full = s_empty + 2;                // 2
+    uint64_t* p_empty = p_full + 2;                // 2
+    uint64_t* g_full = p_empty + 2;                // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctile = blockIdx.x, split = blockIdx.y;
+    const int t_begin = split * ws.tiles_per_split;
+    const int t_end = min(ws.n_tiles, t_begin + ws.tiles_per_split);
+    const int T = t_end - t_begin;                 // >= 1 by construction of the grid
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 4); mbar_init(p_full + i, 4); mbar_init(p_empty + i, 1); }
+        mbar_init(g_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: Q tile once, then the X tile ring =====
+        if (lane == 0) {
+            mbar_expect_tx(q_full, TC_Q_BYTES);
+            bulk_g2s(q_s, ws.qt + (size_t)ctile * TC_Q_BYTES, TC_Q_BYTES, q_full);
+            for (int t = 0; t < T; ++t) {
+                const int s = t % TC_STAGES;
+                if (t >= TC_STAGES) mbar_wait(x_empty + s, ((t / TC_STAGES) - 1) & 1, ws.err, 1);
+                mbar_expect_tx(x_full + s, TC_STAGE_DATA);
+                bulk_g2s(x_s + s * TC_STAGE_BYTES, ws.xt + (size_t)(t_begin + t) * TC_STAGE_DATA, TC_STAGE_DATA, x_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t q_addr = smem_u32(q_s);
+            mbar_wait(q_full, 0, ws.err, 2);
+            tc_fence_after();
+            for (int t = 0; t <= T; ++t) {
+                if (t < T) {
+                    const int s = t % TC_STAGES, b = t & 1;
+                    mbar_wait(x_full + s, (t / TC_STAGES) & 1, ws.err, 3);
+                    if (t >= 2) mbar_wait(s_empty + b, ((t >> 1) - 1) & 1, ws.err, 4);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
+                    const uint32_t d = tmem + TC_COL_S + 64 * b;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {          // Qhi.Xhi, Qlo.Xhi, Qhi.Xlo
+                        const uint32_t qa = q_addr + (pass == 1 ? TC_QPART_BYTES : 0);
+                        const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
+#pragma unroll
+                        for (int j = 0; j < TC_KP / 16; ++j) {
+                            const uint32_t koff = (j & 3) * 32;
+                            const uint64_t ad = make_desc(qa + (j >> 2) * (TC_CHAINS * 128) + koff, 16, 1024);
+                            const uint64_t bd = make_desc(xa + (j >> 2) * (TC_OBS * 128) + koff, 16, 1024);
+                            mma_ss(d, ad, bd, TC_IDESC_G1, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc_commit(s_full + b);
+                }
+                if (t >= 1) {
+                    const int u = t - 1, s = u % TC_STAGES, b = u & 1;
+                    mbar_wait(p_full + b, (u >> 1) & 1, ws.err, 5);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
+                    const uint32_t p_base = tmem + TC_COL_P + 64 * b;
+                    const uint32_t d = tmem + TC_COL_G;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {          // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
+                        const uint32_t pa = p_base + (pass == 1 ? 32 : 0);
+                        const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
+#pragma unroll
+                        for (int j = 0; j < TC_OBS / 16; ++j) {
+                            // MN-major B: 2 feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
+                            const uint64_t bd = make_desc(xa + j * 2048, TC_OBS * 128, 1024);
+                            mma_ts(d, pa + j * 8, bd, TC_IDESC_G2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(x_empty + s);
+                    tc_commit(p_empty + b);
+                    if (u == T - 1) tc_commit(g_full);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warpgroup: thread == chain (TMEM lane) =====
+        const int wq = warp & 3;                                     // TMEM lane quarter of this warp
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        double logp = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const int s = t % TC_STAGES, b = t & 1;
+            const float* ys = reinterpret_cast<const float*>(x_s + s * TC_STAGE_BYTES + 2 * TC_XPART_BYTES);
+            mbar_wait(x_full + s, (t / TC_STAGES) & 1, ws.err, 9);    // y values of this stage (async-proxy writes)
+            mbar_wait(s_full + b, (t >> 1) & 1, ws.err, 6);
+            tc_fence_after();
+            if (t >= 2) mbar_wait(p_empty + b, ((t >> 1) - 1) & 1, ws.err, 7);
+            tc_fence_after();
+            float lsum = 0.f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                TC_LD32(tmem + lane_addr + TC_COL_S + 64 * b + 32 * half, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float r2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float eta = __uint_as_float(v[2 * i + h]);
+                        const float yy = ys[32 * half + 2 * i + h];
+                        const float e = __expf(-fabsf(eta));
+                        const float inv = __frcp_rn(1.f + e);
+                        const float sig = eta >= 0.f ? inv : e * inv;
+                        lsum += yy * eta - (fmaxf(eta, 0.f) + log1pf(e));
+                        r2[h] = yy - sig;
+                    }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
+                    const float2 back = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
+                    hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                TC_ST16(tmem + lane_addr + TC_COL_P + 64 * b + 16 * half, hi);
+                TC_ST16(tmem + lane_addr + TC_COL_P + 64 * b + 32 + 16 * half, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(s_empty + b); mbar_arrive(p_full + b); }
+            logp += (double)lsum;
+        }
+        // the slab's gradient tile: G[chain row][128 features] -> global partials
+        mbar_wait(g_full, 0, ws.err, 8);
+        tc_fence_after();
+        const int chain = ctile * TC_CHAINS + row;
+        float* gout = ws.gpart + ((size_t)split * ws.c_pad + chain) * TC_KP;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t v[32];
+            TC_LD32(tmem + lane_addr + TC_COL_G + 32 * q4, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(gout + 32 * q4)[i] =
+                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+        ws.lpart[(size_t)split * ws.c_pad + chain] = logp;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// fixed-order reduction over slabs + prior + correction for zero-padded rows
+__global__ void k_glm_tc_finalize(TcWorkspace ws, int n_chains, int K1, double prior_tau, const float* qA,
+                                  const float* qB, float* gA, float* gB, int ld, const B2ChainState* st, double* logp) {
+    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (chain >= n_chains) return;
+    int sel = 0;
+    if (st) {
+        if (st[chain].phase > B2_PHASE_HMC) return;
+        sel = st[chain].sel;
+    }
+    const float* q = (sel ? qB : qA) + (size_t)chain * ld;
+    float* g = (sel ? gB : gA) + (size_t)chain * ld;
+    double prior = 0.0;
+    for (int k = lane; k < K1; k += 32) {
+        double s = 0.0;
+        for (int sp = 0; sp < ws.splits; ++sp) s += (double)ws.gpart[((size_t)sp * ws.c_pad + chain) * TC_KP + k];
+        if (k > 0) {
+            const double b = (double)q[k];
+            s -= prior_tau * b;
+            prior += 0.5 * (-prior_tau * b * b + log(prior_tau) - B2_LOG_2PI);
+        }
+        g[k] = (float)s;
+    }
+    double lp = 0.0;
+    for (int sp = lane; sp < ws.splits; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
+    for (int o = 16; o > 0; o >>= 1) {
+        prior += __shfl_xor_sync(0xffffffffu, prior, o);
+        lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    }
+    // zero-padded rows have eta = 0 exactly and contributed -log 2 each
+    if (lane == 0) logp[chain] = lp + prior + (double)ws.n_pad_rows * B2_LOG_2;
+}
+
+// ---------------------------------------------------------------------------------- host
+struct TcHostState {
+    TcWorkspace ws;
+    bool ready;
+};
+
+bool b2_glm_tc_supported(const b2_engine* e) {
+    return e->md.family == B2_FAMILY_GLM_LOGIT && e->dtype == B2_F32 && e->md.G + 1 <= TC_KP && e->md.N >= 1;
+}
+
+static int tc_setup(b2_engine* e, cudaStream_t stream) {
+    TcHostState* hs = new TcHostState();
+    memset(hs, 0, sizeof(*hs));
+    TcWorkspace& w = hs->ws;
+    const int N = e->md.N;
+    w.n_tiles = (N + TC_OBS - 1) / TC_OBS;
+    w.n_pad_rows = w.n_tiles * TC_OBS - N;
+    w.chain_tiles = (e->C + TC_CHAINS - 1) / TC_CHAINS;
+    w.c_pad = w.chain_tiles * TC_CHAINS;
+    int splits = e->sm_count / w.chain_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > w.n_tiles) splits = w.n_tiles;
+    w.tiles_per_split = (w.n_tiles + splits - 1) / splits;
+    w.splits = (w.n_tiles + w.tiles_per_split - 1) / w.tiles_per_split;
+    B2_CUDA_OK(cudaMalloc(&w.xt, (size_t)w.n_tiles * TC_STAGE_DATA));
+    B2_CUDA_OK(cudaMalloc(&w.qt, (size_t)w.chain_tiles * TC_Q_BYTES));
+    B2_CUDA_OK(cudaMalloc(&w.gpart, (size_t)w.splits * w.c_pad * TC_KP * sizeof(float)));
+    B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)w.splits * w.c_pad * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&w.err, sizeof(int)));
+    B2_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), stream));
+    k_glm_tc_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt, w.n_tiles);
+    B2_CUDA_OK(cudaGetLastError());
+    B2_CUDA_OK(cudaFuncSetAttribute(k_glm_tc_main, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    e->launches += 1;
+    hs->ready = true;
+    e->glm_tc = hs;            // owned by the engine; released in b2_glm_tc_release
+    return 0;
+}
+
+void b2_glm_tc_release(b2_engine* e) {
+    if (!e->glm_tc) return;
+    TcHostState* hs = (TcHostState*)e->glm_tc;
+    cudaFree(hs->ws.xt); cudaFree(hs->ws.qt); cudaFree(hs->ws.gpart); cudaFree(hs->ws.lpart); cudaFree(hs->ws.err);
+    delete hs;
+    e->glm_tc = nullptr;
+}
+
+int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
+                     const B2ChainState* st, int n, double* logp, cudaStream_t stream) {
+    if (!e->glm_tc) {
+        int rc = tc_setup(e, stream);
+        if (rc) return rc;
+    }
+    TcHostState* hs = (TcHostState*)e->glm_tc;
+    TcWorkspace& w = hs->ws;
+    const int K1 = e->md.G + 1;
+    k_glm_tc_pack_q<<<w.chain_tiles, 256, 0, stream>>>(qA, qB, ld, st, n, K1, w.qt);
+    dim3 grid(w.chain_tiles, w.splits);
+    k_glm_tc_main<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(w);
+    k_glm_tc_finalize<<<(n + 3) / 4, 128, 0, stream>>>(w, n, K1, e->md.hp[0], qA, qB, gA, gB, ld, st, logp);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 3;
+    return 0;
 }

@@ -39,6 +39,25 @@ def test_logp_dlogp_matches_oracle(name, dtype, tol):
     eng.close()
 
 
+def test_glm_tcgen05_path_matches_oracle():
+    """the tensor-core kernel: 3 row splits x 2 chain tiles, ragged N (zero-padded rows), odd K"""
+    from oracle import densities as od
+    from pymc3_b200 import model as pm
+    for n, k, chains in [(1000 + 37, 13, 70), (5000, 100, 300), (64, 127, 5)]:
+        X, y = models_util.glm_data(n, k, seed=7)
+        model, oracle = pm.LogisticGLM(X, y), od.LogisticGLM(X, y)
+        rng = np.random.default_rng(6)
+        q = (rng.normal(size=(chains, oracle.ndim)) * 0.5).astype("f4")
+        eng = model.engine(chains, dtype="float32")
+        logp, grad = eng.logp_dlogp(q, glm_path=_capi.B2_GLM_TCGEN05)
+        logp, grad = logp.cpu().numpy(), grad.cpu().numpy().astype("f8")
+        for i in range(0, chains, max(1, chains // 16)):
+            l0, g0 = oracle(q[i].astype("f8"))
+            assert abs(logp[i] - l0) <= 1e-4 * abs(l0), (n, k, i, logp[i], l0)
+            assert _rel(grad[i], g0) <= 1e-4, (n, k, i, _rel(grad[i], g0))
+        eng.close()
+
+
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-6), ("float32", 1e-4)])
 @pytest.mark.parametrize("path", [_capi.B2_GLM_GROUP, _capi.B2_GLM_SIMT])
 def test_glm_chain_batched_paths(dtype, tol, path):
