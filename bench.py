@@ -238,24 +238,24 @@ def run_b200(args):
 
     # ---- pass A: data and chain state resident in HBM
     eng = new_engine()
-    trace_chunks = []
+    trace = eng.alloc_trace(_capi.B2_NUTS, total)          # the whole job's device trace, allocated up front
     barrier()
     tw0 = time.perf_counter()
     for s in range(W):
-        trace_chunks.append(eng.run(_capi.B2_NUTS, ips, tune, opts))
+        eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=s * ips)
     torch.cuda.synchronize(dev)
     wall_warm = time.perf_counter() - tw0
     clocks = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         clocks.start()
-    eng.set_profiling(True)
+    eng.set_profiling(not args.no_profile)
     launches0 = eng.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
     for s in range(K):
-        trace_chunks.append(eng.run(_capi.B2_NUTS, ips, tune, opts))
+        eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=(W + s) * ips)
     ev1.record()
     barrier()
     wall_timed = time.perf_counter() - t0
@@ -267,7 +267,7 @@ def run_b200(args):
     failed = sum(1 for r in reports if r.phase != _capi.PHASE_DONE)
     eng.close()
 
-    tree = torch.cat([c["tree_size"] for c in trace_chunks])            # [total, C]
+    tree = trace["tree_size"]                                           # [total, C]
     leap_timed = int(tree[W * ips:].sum().item())
     leap_all = int(tree.sum().item())
     t_vec = torch.tensor([dev_ms / 1e3, wall_timed, wall_warm], dtype=torch.float64, device=dev)
@@ -281,7 +281,7 @@ def run_b200(args):
     # ---- min bulk ESS over every scalar of every free and back-transformed variable (post-tune draws)
     ess_info = None
     if not args.skip_ess and total - tune >= 100:
-        q = torch.cat([c["q"] for c in trace_chunks])[tune:]               # [draws, C, D]
+        q = trace["q"][tune:]                                              # [draws, C, D]
         q = q.permute(1, 0, 2).contiguous().cpu().numpy().astype("f8")      # [C, draws, D]
         vals = model.expand(q)
         ess_vec = np.concatenate([np.ravel(b2stats.ess(v)) for v in vals.values()])
@@ -289,7 +289,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(ess_t, op=dist.ReduceOp.SUM)                    # independent chain sets add
         ess_info = {"min_bulk_ess": float(ess_t.min().item()), "n_scalars": int(ess_t.numel())}
-    del trace_chunks
+    del trace
 
     # ---- pass B: end to end -- every step uploads its inputs from pinned host memory and reads
     #      its trace + stats back into pinned host memory (same seeds => same job)
@@ -413,6 +413,8 @@ def main():
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--glm-path", default="auto", choices=["auto", "group", "simt", "tcgen05"])
     ap.add_argument("--skip-ess", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="do not time individual likelihood launches")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline sampling")

@@ -190,7 +190,13 @@ class _Trajectory:
     def summary(self):                                           # :391-406
         mean_accept = 0.0
         if self.log_size > 0:
-            mean_accept = np.exp(self.log_accept) / np.expm1(self.log_size)
+            with np.errstate(over="ignore", invalid="ignore"):
+                mean_accept = np.exp(self.log_accept) / np.expm1(self.log_size)
+            if not np.isfinite(mean_accept):
+                # NOT in the reference: there exp()/expm1() overflows to inf/inf = NaN once the energy
+                # drops by more than ~709 (< Emax) and dual averaging is NaN from then on.  The engine
+                # evaluates the same ratio in log space in exactly that case (deviations).
+                mean_accept = np.exp(self.log_accept - (self.log_size + np.log1p(-np.exp(-self.log_size))))
         return {
             "depth": self.depth,
             "mean_tree_accept": mean_accept,

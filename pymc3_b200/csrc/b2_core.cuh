@@ -572,7 +572,14 @@ B2_HD bool b2_advance(const G& g, const B2View<T>& w, int c, B2ChainState& s, do
     if (act == B2_ACT_TOP_MERGE) act = b2_top_merge(g, w, c, s);
     if (act == B2_ACT_END_NUTS || act == B2_ACT_END_NUTS_MAXDEPTH) {
         es.accept_stat = 0.0;                             // nuts.py:391-397
-        if (s.log_size > 0.0) es.accept_stat = exp(s.log_accept) / expm1(s.log_size);
+        if (s.log_size > 0.0) {
+            es.accept_stat = exp(s.log_accept) / expm1(s.log_size);
+            // Deliberate deviation: for energy drops > ~709 (still below Emax = 1000) the reference's
+            // exp()/expm1() is inf/inf = NaN, which poisons dual averaging for the rest of the chain.
+            // Same quantity in log space, used only where the reference's expression is not finite.
+            if (!b2_finite(es.accept_stat))
+                es.accept_stat = exp(s.log_accept - (s.log_size + log1p(-exp(-s.log_size))));
+        }
         if (act == B2_ACT_END_NUTS_MAXDEPTH && !(s.iter < w.tune_until)) s.n_maxdepth_post += 1;   // nuts.py:182-184
         s.cur_logp = s.prop_logp;
         es.energy = s.prop_energy; es.energy_error = s.prop_energy - s.e0; es.model_logp = s.prop_logp;

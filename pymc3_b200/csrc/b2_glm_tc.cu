@@ -17,7 +17,9 @@
 // build into the exact 128B-swizzled shared-memory image the UMMA descriptors expect, so a pipeline
 // stage is one contiguous 33 KB copy and no tensor map is needed.  Accumulators live in TMEM
 // (S double-buffered 2x64 cols, R 2x64 cols, G 128 cols).  Warp roles: 0 = bulk-copy producer,
-// 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..7 = epilogue warpgroup (lane == chain).
+// 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..19 = four epilogue warpgroups (TMEM lane ==
+// chain; warpgroup g takes observation columns 16g..16g+15 of every tile, so each SM sub-partition
+// always has four epilogue warps to interleave -- one warp per scheduler was latency-bound, ncu r1).
 #include <cuda_bf16.h>
 #include <cstring>
 #include "b2_engine.cuh"
@@ -32,7 +34,9 @@
 #define TC_QPART_BYTES (TC_CHAINS * TC_KP * 2)         // 32768
 #define TC_Q_BYTES (2 * TC_QPART_BYTES)                // 65536
 #define TC_SMEM_BYTES (1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256)
-#define TC_THREADS 256
+#define TC_EPI_GROUPS 4               // epilogue warpgroups; group g owns observation columns 16g..16g+15 of a tile
+#define TC_EPI_WARPS (4 * TC_EPI_GROUPS)
+#define TC_THREADS (128 + 32 * TC_EPI_WARPS)
 #define TC_TMEM_COLS 512
 #define TC_COL_S 0                    // S[b] at 64 b
 #define TC_COL_P 128                  // P[b] at 128 + 64 b   (hi: 32 cols, lo: 32 cols; 2 bf16 per column)
@@ -42,7 +46,7 @@ struct TcWorkspace {
     unsigned char* xt;       // [n_tiles][TC_STAGE_DATA] pre-swizzled X tiles (+ y)
     unsigned char* qt;       // [chain_tiles][TC_Q_BYTES] swizzled Q tiles, rewritten every launch
     float* gpart;            // [splits][c_pad][TC_KP]
-    double* lpart;           // [splits][c_pad]
+    double* lpart;           // [splits][TC_EPI_GROUPS][c_pad]
     int n_tiles, c_pad, chain_tiles, splits, tiles_per_split, n_pad_rows;
     int* err;                // device watchdog flag
 };
@@ -83,7 +87,7 @@ __global__ void k_glm_tc_pack_q(const float* qA, const float* qB, int ld, const 
                                 int K1, unsigned char* __restrict__ qt) {
     const int ctile = blockIdx.x;
     unsigned char* blob = qt + (size_t)ctile * TC_Q_BYTES;
-    for (int idx = threadIdx.x; idx < TC_CHAINS * TC_KP; idx += blockDim.x) {
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < TC_CHAINS * TC_KP; idx += gridDim.y * blockDim.x) {
         const int r = idx / TC_KP, c = idx - r * TC_KP;
         const int chain = ctile * TC_CHAINS + r;
         float v = 0.f;
@@ -169,6 +173,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory")
 
+#define TC_LD16(taddr, v)                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                  \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                          \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),       \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])  \
+                 : "r"(taddr) : "memory")
+#define TC_ST8(taddr, v)                                                                                    \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                   \
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory")
+__device__ __forceinline__ float tc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tc_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tc_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // instruction descriptors (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16
 #define TC_IDESC_BASE ((1u << 4) | (1u << 7) | (1u << 10))
 #define TC_IDESC_G1 (TC_IDESC_BASE | ((TC_OBS >> 3) << 17) | ((TC_CHAINS >> 4) << 24))               // N=64,  K-major B
@@ -199,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 4); mbar_init(p_full + i, 4); mbar_init(p_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TC_EPI_WARPS); mbar_init(p_full + i, TC_EPI_WARPS); mbar_init(p_empty + i, 1); }
         mbar_init(g_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -279,71 +296,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue warpgroup: thread == chain (TMEM lane) =====
-        const int wq = warp & 3;                                     // TMEM lane quarter of this warp
+        // ===== epilogue warpgroups: thread == (chain row, 16-observation column group) =====
+        const int wq = warp & 3;                                     // TMEM lane quarter this warp may touch
+        const int cg = (warp - 4) >> 2;                              // column group 0..3
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         double logp = 0.0;
         for (int t = 0; t < T; ++t) {
             const int s = t % TC_STAGES, b = t & 1;
-            const float* ys = reinterpret_cast<const float*>(x_s + s * TC_STAGE_BYTES + 2 * TC_XPART_BYTES);
+            const float4* ys4 = reinterpret_cast<const float4*>(x_s + s * TC_STAGE_BYTES + 2 * TC_XPART_BYTES) + 4 * cg;
             mbar_wait(x_full + s, (t / TC_STAGES) & 1, ws.err, 9);    // y values of this stage (async-proxy writes)
             mbar_wait(s_full + b, (t >> 1) & 1, ws.err, 6);
             tc_fence_after();
-            if (t >= 2) mbar_wait(p_empty + b, ((t >> 1) - 1) & 1, ws.err, 7);
-            tc_fence_after();
+            uint32_t v[16];
+            TC_LD16(tmem + lane_addr + TC_COL_S + 64 * b + 16 * cg, v);
+            float yv[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 y4 = ys4[i];
+                yv[4 * i] = y4.x; yv[4 * i + 1] = y4.y; yv[4 * i + 2] = y4.z; yv[4 * i + 3] = y4.w;
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + b);                 // S(t) is in registers: GEMM1(t+2) may overwrite it
+            uint32_t hi[8], lo[8];
             float lsum = 0.f;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                TC_LD32(tmem + lane_addr + TC_COL_S + 64 * b + 32 * half, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint32_t hi[16], lo[16];
+            for (int i = 0; i < 8; ++i) {
+                float r2[2];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float r2[2];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float eta = __uint_as_float(v[2 * i + h]);
-                        const float yy = ys[32 * half + 2 * i + h];
-                        const float e = __expf(-fabsf(eta));
-                        const float inv = __frcp_rn(1.f + e);
-                        const float sig = eta >= 0.f ? inv : e * inv;
-                        lsum += yy * eta - (fmaxf(eta, 0.f) + log1pf(e));
-                        r2[h] = yy - sig;
-                    }
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
-                    const float2 back = __bfloat1622float2(h2);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
-                    hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                    lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                for (int h = 0; h < 2; ++h) {
+                    const float eta = __uint_as_float(v[2 * i + h]);
+                    const float yy = yv[2 * i + h];
+                    const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
+                    const float w1 = 1.f + e;
+                    const float inv = tc_rcp(w1);
+                    const float sig = eta >= 0.f ? inv : e * inv;
+                    // y*eta - softplus(eta),  softplus = max(eta,0) + log(1 + exp(-|eta|))
+                    lsum += fmaf(yy, eta, -fmaf(0.6931471805599453f, tc_lg2(w1), fmaxf(eta, 0.f)));
+                    r2[h] = yy - sig;
                 }
-                TC_ST16(tmem + lane_addr + TC_COL_P + 64 * b + 16 * half, hi);
-                TC_ST16(tmem + lane_addr + TC_COL_P + 64 * b + 32 + 16 * half, lo);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
+                const float2 back = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
+                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
             }
+            if (t >= 2) mbar_wait(p_empty + b, ((t >> 1) - 1) & 1, ws.err, 7);
+            tc_fence_after();
+            TC_ST8(tmem + lane_addr + TC_COL_P + 64 * b + 8 * cg, hi);
+            TC_ST8(tmem + lane_addr + TC_COL_P + 64 * b + 32 + 8 * cg, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(s_empty + b); mbar_arrive(p_full + b); }
+            if (lane == 0) mbar_arrive(p_full + b);
             logp += (double)lsum;
         }
-        // the slab's gradient tile: G[chain row][128 features] -> global partials
+        // the slab's gradient tile: G[chain row][128 features] -> global partials (32 columns per group)
         mbar_wait(g_full, 0, ws.err, 8);
         tc_fence_after();
         const int chain = ctile * TC_CHAINS + row;
-        float* gout = ws.gpart + ((size_t)split * ws.c_pad + chain) * TC_KP;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t v[32];
-            TC_LD32(tmem + lane_addr + TC_COL_G + 32 * q4, v);
+        float* gout = ws.gpart + ((size_t)split * ws.c_pad + chain) * TC_KP + 32 * cg;
+        {
+            uint32_t g32[32];
+            TC_LD32(tmem + lane_addr + TC_COL_G + 32 * cg, g32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(gout + 32 * q4)[i] =
-                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                reinterpret_cast<float4*>(gout)[i] =
+                    make_float4(__uint_as_float(g32[4 * i]), __uint_as_float(g32[4 * i + 1]),
+                                __uint_as_float(g32[4 * i + 2]), __uint_as_float(g32[4 * i + 3]));
         }
-        ws.lpart[(size_t)split * ws.c_pad + chain] = logp;
+        // logp partial of this column group; the finalize kernel adds the TC_EPI_GROUPS partials
+        ws.lpart[((size_t)split * TC_EPI_GROUPS + cg) * ws.c_pad + chain] = logp;
     }
     tc_fence_before();
     __syncthreads();
@@ -378,7 +404,7 @@ __global__ void k_glm_tc_finalize(TcWorkspace ws, int n_chains, int K1, double p
         g[k] = (float)s;
     }
     double lp = 0.0;
-    for (int sp = lane; sp < ws.splits; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
+    for (int sp = lane; sp < ws.splits * TC_EPI_GROUPS; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
     for (int o = 16; o > 0; o >>= 1) {
         prior += __shfl_xor_sync(0xffffffffu, prior, o);
         lp += __shfl_xor_sync(0xffffffffu, lp, o);
@@ -414,7 +440,7 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     B2_CUDA_OK(cudaMalloc(&w.xt, (size_t)w.n_tiles * TC_STAGE_DATA));
     B2_CUDA_OK(cudaMalloc(&w.qt, (size_t)w.chain_tiles * TC_Q_BYTES));
     B2_CUDA_OK(cudaMalloc(&w.gpart, (size_t)w.splits * w.c_pad * TC_KP * sizeof(float)));
-    B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)w.splits * w.c_pad * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)w.splits * TC_EPI_GROUPS * w.c_pad * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&w.err, sizeof(int)));
     B2_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), stream));
     k_glm_tc_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt, w.n_tiles);
@@ -443,7 +469,7 @@ int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, 
     TcHostState* hs = (TcHostState*)e->glm_tc;
     TcWorkspace& w = hs->ws;
     const int K1 = e->md.G + 1;
-    k_glm_tc_pack_q<<<w.chain_tiles, 256, 0, stream>>>(qA, qB, ld, st, n, K1, w.qt);
+    k_glm_tc_pack_q<<<dim3(w.chain_tiles, 16), 256, 0, stream>>>(qA, qB, ld, st, n, K1, w.qt);
     dim3 grid(w.chain_tiles, w.splits);
     k_glm_tc_main<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(w);
     k_glm_tc_finalize<<<(n + 3) / 4, 128, 0, stream>>>(w, n, K1, e->md.hp[0], qA, qB, gA, gB, ld, st, logp);

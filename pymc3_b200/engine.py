@@ -108,23 +108,35 @@ class Engine:
         self.torch.cuda.synchronize(self.dev)
 
     # -- the draw loop for all chains (sampling.py:914-936)
-    def run(self, kind, n_iters, tune_until, opts, trace_q=True):
-        """Runs `n_iters` transitions; returns {'q': [n, C, D], stat: [n, C]} device tensors."""
+    def alloc_trace(self, kind, n_iters, trace_q=True):
+        """Device trace buffers for `n_iters` iterations: {'q': [n, C, D], stat: [n, C]}."""
         torch = self.torch
         names = _NUTS_STATS if kind == _capi.B2_NUTS else _HMC_STATS
-        out, tr = {}, _capi.TraceOut()
+        out = {}
         if trace_q:
             out["q"] = torch.empty((n_iters, self.n_chains, self.D), dtype=self.t_dtype, device=self.dev)
-            tr.d_q = out["q"].data_ptr()
         for name, code in names.items():
-            t = torch.zeros((n_iters, self.n_chains), device=self.dev,
-                            dtype={"f8": torch.float64, "i4": torch.int32, "u1": torch.uint8}[code])
-            out[name] = t
+            out[name] = torch.zeros((n_iters, self.n_chains), device=self.dev,
+                                    dtype={"f8": torch.float64, "i4": torch.int32, "u1": torch.uint8}[code])
+        return out
+
+    def run(self, kind, n_iters, tune_until, opts, trace_q=True, out=None, row0=0):
+        """Runs `n_iters` transitions of every chain; returns {'q': [n, C, D], stat: [n, C]} device
+        tensors.  With `out` (from alloc_trace) the rows [row0, row0 + n_iters) of those buffers are
+        filled instead of allocating (chunked runs of one long job)."""
+        if out is None:
+            out = self.alloc_trace(kind, n_iters, trace_q)
+            view = out
+        else:
+            view = {k: v[row0:row0 + n_iters] for k, v in out.items()}
+        tr = _capi.TraceOut()
+        for name, t in view.items():
+            assert t.is_contiguous() and t.shape[0] == n_iters
             setattr(tr, "d_" + name, t.data_ptr())
         o = _capi.SamplerOpts(kind=kind, n_iters=int(n_iters), tune_until=int(tune_until), **opts)
         _capi.check(self.lib.b2_sample_run(self.handle, C.byref(o), C.byref(tr), self._stream()), self.lib)
         self.iter_done += int(n_iters)
-        return out
+        return view
 
     def reports(self):
         arr = (_capi.ChainReport * self.n_chains)()
