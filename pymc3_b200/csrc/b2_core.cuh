@@ -98,6 +98,10 @@ struct B2View {
     B2_HD T* S(int buf, int which, int c) const { return V(B2_V_STACK0 + buf * B2_S_NVEC + which, c); }
 };
 
+B2_HD bool b2_needs_grad(int phase) {
+    return phase == B2_PHASE_INIT || phase == B2_PHASE_TREE || phase == B2_PHASE_HMC;
+}
+
 // ----------------------------------------------------------------------------- thread groups
 struct B2HostGroup {                       // tests only: one "lane"
     static constexpr int NT = 1;

@@ -36,10 +36,6 @@ __global__ void k_init_chains(B2View<T> w, const T* q0, const unsigned long long
     if (g.lane() == 0) w.st[c] = s;
 }
 
-__device__ __forceinline__ bool b2_needs_grad(int phase) {
-    return phase == B2_PHASE_INIT || phase == B2_PHASE_TREE || phase == B2_PHASE_HMC;
-}
-
 // group-per-chain likelihood (parity hook, small models in lock-step mode, cross-check)
 template <typename T, typename G>
 __device__ __forceinline__ void logp_group_body(const G& g, const B2ModelData& m, const T* qA, const T* qB,
@@ -403,20 +399,34 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         const T* qA = w.V(B2_V_QE0, 0); const T* qB = w.V(B2_V_QE1, 0);
         T* gA = w.V(B2_V_GE0, 0); T* gB = w.V(B2_V_GE1, 0);
         const int batch = 32;
+        // GLM on the tensor-core path: {tcgen05 likelihood, fused finalize+advance+repack} per step
+        const bool fused_tc = sizeof(T) == 4 && !blk && e->md.family == B2_FAMILY_GLM_LOGIT &&
+                              pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05;
+        if (fused_tc && !b2_glm_tc_supported(e)) { b2_set_error("tcgen05 GLM path does not support this shape"); return -6; }
         if (e->iter_done > 0) {                       // re-activate chains that finished the previous call
             if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 1);
             else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 1);
             e->launches += 1;
         }
+        if (fused_tc) {
+            int rc = b2_glm_tc_pack(e, (const float*)qA, (const float*)qB, e->Dp, e->st, e->C, s);
+            if (rc) return rc;
+        }
         for (;;) {
             for (int b = 0; b < batch; ++b) {
                 if (e->profile) cudaEventRecord(e->ev[2 * b], s);
-                int rc = launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
+                int rc = fused_tc ? b2_glm_tc_main(e, s)
+                                  : launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
                 if (rc) return rc;
                 if (e->profile) cudaEventRecord(e->ev[2 * b + 1], s);
-                if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 0);
-                else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 0);
-                e->launches += 1;
+                if (fused_tc) {
+                    rc = b2_glm_tc_post(e, &w, s);
+                    if (rc) return rc;
+                } else {
+                    if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 0);
+                    else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 0);
+                    e->launches += 1;
+                }
             }
             B2_CUDA_OK(cudaMemsetAsync(e->d_active, 0, sizeof(int), s));
             k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, e->d_active);

@@ -53,6 +53,11 @@ int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, 
                      const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);
 bool b2_glm_tc_supported(const b2_engine* e);
 void b2_glm_tc_release(b2_engine* e);
+// fused lock-step pieces of the tensor-core path: split/swizzle the pending positions, run the
+// likelihood, then {reduce slab partials, advance the chain state machine, re-split} in one kernel
+int b2_glm_tc_pack(b2_engine* e, const float* qA, const float* qB, int ld, const B2ChainState* st, int n, cudaStream_t s);
+int b2_glm_tc_main(b2_engine* e, cudaStream_t s);
+int b2_glm_tc_post(b2_engine* e, const void* view_f32, cudaStream_t s);
 template <typename T>
 int b2_hier_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
                    const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);

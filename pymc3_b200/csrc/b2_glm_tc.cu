@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TC_EPI_WARPS); mbar_init(p_full + i, TC_EPI_WARPS); mbar_init(p_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TC_EPI_WARPS / 2); mbar_init(p_full + i, TC_EPI_WARPS / 2); mbar_init(p_empty + i, 1); }
         mbar_init(g_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -301,52 +301,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
         const int cg = (warp - 4) >> 2;                              // column group 0..3
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        // Column groups {0,1} take even tiles, {2,3} odd tiles (32 observation columns per warp and
+        // tile): the two pairs run one tile apart, so MUFU-heavy math of one pair overlaps the TMEM
+        // loads / stores / barrier waits of the other instead of all 16 warps marching in lock-step.
+        const int pair = cg >> 1, sub = cg & 1;
         double logp = 0.0;
-        for (int t = 0; t < T; ++t) {
-            const int s = t % TC_STAGES, b = t & 1;
-            const float4* ys4 = reinterpret_cast<const float4*>(x_s + s * TC_STAGE_BYTES + 2 * TC_XPART_BYTES) + 4 * cg;
+        for (int t = pair; t < T; t += 2) {
+            const int s = t % TC_STAGES, b = pair;
+            const float4* ys4 = reinterpret_cast<const float4*>(x_s + s * TC_STAGE_BYTES + 2 * TC_XPART_BYTES) + 8 * sub;
             mbar_wait(x_full + s, (t / TC_STAGES) & 1, ws.err, 9);    // y values of this stage (async-proxy writes)
             mbar_wait(s_full + b, (t >> 1) & 1, ws.err, 6);
             tc_fence_after();
-            uint32_t v[16];
-            TC_LD16(tmem + lane_addr + TC_COL_S + 64 * b + 16 * cg, v);
-            float yv[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 y4 = ys4[i];
-                yv[4 * i] = y4.x; yv[4 * i + 1] = y4.y; yv[4 * i + 2] = y4.z; yv[4 * i + 3] = y4.w;
-            }
+            uint32_t v[2][16];
+            TC_LD16(tmem + lane_addr + TC_COL_S + 64 * b + 32 * sub, v[0]);
+            TC_LD16(tmem + lane_addr + TC_COL_S + 64 * b + 32 * sub + 16, v[1]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + b);                 // S(t) is in registers: GEMM1(t+2) may overwrite it
-            uint32_t hi[8], lo[8];
+            uint32_t hi[2][8], lo[2][8];
             float lsum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float r2[2];
+            for (int hh = 0; hh < 2; ++hh) {
+                float yv[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float eta = __uint_as_float(v[2 * i + h]);
-                    const float yy = yv[2 * i + h];
-                    const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
-                    const float w1 = 1.f + e;
-                    const float inv = tc_rcp(w1);
-                    const float sig = eta >= 0.f ? inv : e * inv;
-                    // y*eta - softplus(eta),  softplus = max(eta,0) + log(1 + exp(-|eta|))
-                    lsum += fmaf(yy, eta, -fmaf(0.6931471805599453f, tc_lg2(w1), fmaxf(eta, 0.f)));
-                    r2[h] = yy - sig;
+                for (int i = 0; i < 4; ++i) {
+                    const float4 y4 = ys4[4 * hh + i];
+                    yv[4 * i] = y4.x; yv[4 * i + 1] = y4.y; yv[4 * i + 2] = y4.z; yv[4 * i + 3] = y4.w;
                 }
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
-                const float2 back = __bfloat1622float2(h2);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
-                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float r2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float eta = __uint_as_float(v[hh][2 * i + h]);
+                        const float yy = yv[2 * i + h];
+                        const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
+                        const float w1 = 1.f + e;
+                        const float inv = tc_rcp(w1);
+                        const float sig = eta >= 0.f ? inv : e * inv;
+                        // y*eta - softplus(eta),  softplus = max(eta,0) + log(1 + exp(-|eta|))
+                        lsum += fmaf(yy, eta, -fmaf(0.6931471805599453f, tc_lg2(w1), fmaxf(eta, 0.f)));
+                        r2[h] = yy - sig;
+                    }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
+                    const float2 back = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
+                    hi[hh][i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[hh][i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
             }
             if (t >= 2) mbar_wait(p_empty + b, ((t >> 1) - 1) & 1, ws.err, 7);
             tc_fence_after();
-            TC_ST8(tmem + lane_addr + TC_COL_P + 64 * b + 8 * cg, hi);
-            TC_ST8(tmem + lane_addr + TC_COL_P + 64 * b + 32 + 8 * cg, lo);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                TC_ST8(tmem + lane_addr + TC_COL_P + 64 * b + 16 * sub + 8 * hh, hi[hh]);
+                TC_ST8(tmem + lane_addr + TC_COL_P + 64 * b + 32 + 16 * sub + 8 * hh, lo[hh]);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
@@ -379,7 +390,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     }
 }
 
-// fixed-order reduction over slabs + prior + correction for zero-padded rows
+// fixed-order reduction over slabs + prior + correction for zero-padded rows, for one chain per warp.
+// lane l owns features 4l..4l+3 (one float4 per slab partial).
+__device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int chain, int lane, int K1, double prior_tau,
+                                                    const float* q, float* g) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* gp = reinterpret_cast<const float4*>(ws.gpart + (size_t)chain * TC_KP) + lane;
+    const size_t stride4 = (size_t)ws.c_pad * TC_KP / 4;
+#pragma unroll 6
+    for (int sp = 0; sp < ws.splits; ++sp) {
+        const float4 v = gp[sp * stride4];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+    double prior = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = 4 * lane + j;
+        if (k < K1) {
+            double sgrad = (double)a4[j];
+            if (k > 0) {
+                const double b = (double)q[k];
+                sgrad -= prior_tau * b;
+                prior += 0.5 * (-prior_tau * b * b + log(prior_tau) - B2_LOG_2PI);
+            }
+            g[k] = (float)sgrad;
+        }
+    }
+    double lp = 0.0;
+    for (int sp = lane; sp < ws.splits * TC_EPI_GROUPS; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
+    for (int o = 16; o > 0; o >>= 1) {
+        prior += __shfl_xor_sync(0xffffffffu, prior, o);
+        lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    }
+    // zero-padded rows have eta = 0 exactly and contributed -log 2 each
+    return lp + prior + (double)ws.n_pad_rows * B2_LOG_2;
+}
+
+// bf16 hi/lo split of one chain's position into its row of the swizzled Q tile (lane l: features 4l..4l+3)
+__device__ __forceinline__ void tc_pack_chain(const TcWorkspace& ws, int chain, int lane, int K1, const float* q, bool live) {
+    unsigned char* blob = ws.qt + (size_t)(chain / TC_CHAINS) * TC_Q_BYTES;
+    const int r = chain % TC_CHAINS;
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = 4 * lane + j;
+        const float v = (live && c < K1) ? q[c] : 0.f;
+        hi[j] = __float2bfloat16_rn(v);
+        lo[j] = __float2bfloat16_rn(v - __bfloat162float(hi[j]));
+    }
+    const int c0 = 4 * lane;                   // 4 consecutive columns stay inside one 16-byte swizzle chunk
+    const int off = (c0 >> 6) * (TC_CHAINS * 128) + tc_swz(r, c0 & 63);
+    *reinterpret_cast<uint2*>(blob + off) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(blob + TC_QPART_BYTES + off) = *reinterpret_cast<const uint2*>(lo);
+}
+
 __global__ void k_glm_tc_finalize(TcWorkspace ws, int n_chains, int K1, double prior_tau, const float* qA,
                                   const float* qB, float* gA, float* gB, int ld, const B2ChainState* st, double* logp) {
     const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -392,25 +457,28 @@ __global__ void k_glm_tc_finalize(TcWorkspace ws, int n_chains, int K1, double p
     }
     const float* q = (sel ? qB : qA) + (size_t)chain * ld;
     float* g = (sel ? gB : gA) + (size_t)chain * ld;
-    double prior = 0.0;
-    for (int k = lane; k < K1; k += 32) {
-        double s = 0.0;
-        for (int sp = 0; sp < ws.splits; ++sp) s += (double)ws.gpart[((size_t)sp * ws.c_pad + chain) * TC_KP + k];
-        if (k > 0) {
-            const double b = (double)q[k];
-            s -= prior_tau * b;
-            prior += 0.5 * (-prior_tau * b * b + log(prior_tau) - B2_LOG_2PI);
-        }
-        g[k] = (float)s;
-    }
-    double lp = 0.0;
-    for (int sp = lane; sp < ws.splits * TC_EPI_GROUPS; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
-    for (int o = 16; o > 0; o >>= 1) {
-        prior += __shfl_xor_sync(0xffffffffu, prior, o);
-        lp += __shfl_xor_sync(0xffffffffu, lp, o);
-    }
-    // zero-padded rows have eta = 0 exactly and contributed -log 2 each
-    if (lane == 0) logp[chain] = lp + prior + (double)ws.n_pad_rows * B2_LOG_2;
+    const double lp = tc_finalize_chain(ws, chain, lane, K1, prior_tau, q, g);
+    if (lane == 0) logp[chain] = lp;
+}
+
+// Lock-step companion of k_glm_tc_main: one warp per chain does
+//   slab reduction (-> logp, grad)  ->  b2_advance (the whole NUTS/HMC bookkeeping for this leapfrog)
+//   ->  bf16 hi/lo re-split of the next pending position into the swizzled Q tile.
+// Replaces three launches (finalize, advance, pack) and the round trip of the gradient through HBM.
+__global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double prior_tau) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= w.C) return;
+    B2WarpGroup g;
+    B2ChainState s = w.st[c];
+    if (!b2_needs_grad(s.phase)) return;
+    const float* q = w.V(B2_V_QE0 + s.sel, c);
+    float* gr = w.V(B2_V_GE0 + s.sel, c);
+    const double lp = tc_finalize_chain(ws, c, g.lane(), K1, prior_tau, q, gr);
+    __syncwarp();
+    const bool active = b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
+    if (g.lane() == 0) w.st[c] = s;
+    __syncwarp();
+    if (active) tc_pack_chain(ws, c, g.lane(), K1, w.V(B2_V_QE0 + s.sel, c), true);
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -439,6 +507,7 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     w.splits = (w.n_tiles + w.tiles_per_split - 1) / w.tiles_per_split;
     B2_CUDA_OK(cudaMalloc(&w.xt, (size_t)w.n_tiles * TC_STAGE_DATA));
     B2_CUDA_OK(cudaMalloc(&w.qt, (size_t)w.chain_tiles * TC_Q_BYTES));
+    B2_CUDA_OK(cudaMemsetAsync(w.qt, 0, (size_t)w.chain_tiles * TC_Q_BYTES, stream));
     B2_CUDA_OK(cudaMalloc(&w.gpart, (size_t)w.splits * w.c_pad * TC_KP * sizeof(float)));
     B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)w.splits * TC_EPI_GROUPS * w.c_pad * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&w.err, sizeof(int)));
@@ -460,20 +529,46 @@ void b2_glm_tc_release(b2_engine* e) {
     e->glm_tc = nullptr;
 }
 
+static int tc_ensure(b2_engine* e, cudaStream_t stream) {
+    if (!e->glm_tc) return tc_setup(e, stream);
+    return 0;
+}
+
+int b2_glm_tc_pack(b2_engine* e, const float* qA, const float* qB, int ld, const B2ChainState* st, int n, cudaStream_t stream) {
+    int rc = tc_ensure(e, stream);
+    if (rc) return rc;
+    TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
+    k_glm_tc_pack_q<<<dim3(w.chain_tiles, 16), 256, 0, stream>>>(qA, qB, ld, st, n, e->md.G + 1, w.qt);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return 0;
+}
+
+int b2_glm_tc_main(b2_engine* e, cudaStream_t stream) {
+    TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
+    k_glm_tc_main<<<dim3(w.chain_tiles, w.splits), TC_THREADS, TC_SMEM_BYTES, stream>>>(w);
+    e->launches += 1;
+    return 0;
+}
+
+int b2_glm_tc_post(b2_engine* e, const void* view_f32, cudaStream_t stream) {
+    TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
+    const B2View<float>& v = *reinterpret_cast<const B2View<float>*>(view_f32);
+    k_glm_tc_post<<<(e->C + 3) / 4, 128, 0, stream>>>(w, v, e->md.G + 1, e->md.hp[0]);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return 0;
+}
+
 int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
                      const B2ChainState* st, int n, double* logp, cudaStream_t stream) {
-    if (!e->glm_tc) {
-        int rc = tc_setup(e, stream);
-        if (rc) return rc;
-    }
-    TcHostState* hs = (TcHostState*)e->glm_tc;
-    TcWorkspace& w = hs->ws;
-    const int K1 = e->md.G + 1;
-    k_glm_tc_pack_q<<<dim3(w.chain_tiles, 16), 256, 0, stream>>>(qA, qB, ld, st, n, K1, w.qt);
-    dim3 grid(w.chain_tiles, w.splits);
-    k_glm_tc_main<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(w);
-    k_glm_tc_finalize<<<(n + 3) / 4, 128, 0, stream>>>(w, n, K1, e->md.hp[0], qA, qB, gA, gB, ld, st, logp);
+    int rc = b2_glm_tc_pack(e, qA, qB, ld, st, n, stream);
+    if (rc) return rc;
+    rc = b2_glm_tc_main(e, stream);
+    if (rc) return rc;
+    TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
+    k_glm_tc_finalize<<<(n + 3) / 4, 128, 0, stream>>>(w, n, e->md.G + 1, e->md.hp[0], qA, qB, gA, gB, ld, st, logp);
     B2_CUDA_OK(cudaGetLastError());
-    e->launches += 3;
+    e->launches += 1;
     return 0;
 }

@@ -261,3 +261,29 @@ def test_chunked_runs_continue_the_same_chains(exec_mode):
     assert tune[:40].all() and not tune[40:].any()
     assert all(r.iter == 60 for r in eng.reports())
     eng.close()
+
+
+def test_fused_tensor_core_lockstep_agrees_with_simt_lockstep():
+    """fp32 NUTS on a GLM big enough for the chain-batched kernels: the fused tcgen05 step
+    ({likelihood, finalize+advance+repack}) against the SIMT path -- same decisions early on,
+    same posterior summaries later (round-off separates individual trajectories)."""
+    from pymc3_b200 import model as pm
+    X, y = models_util.glm_data(6000, 20, seed=11)
+    model = pm.LogisticGLM(X, y)
+    D, C = 21, 256
+    rng = np.random.default_rng(3)
+    q0 = rng.uniform(-0.2, 0.2, size=(C, D))
+    seeds = np.arange(C) + 1000
+    runs = {}
+    for name, path in (("tc", _capi.B2_GLM_TCGEN05), ("simt", _capi.B2_GLM_SIMT)):
+        runs[name] = _run_engine(model, q0, seeds, 300, 150, _capi.B2_NUTS, "float32", _capi.B2_EXEC_LOCKSTEP,
+                                 glm_path=path)
+    a, b = runs["tc"], runs["simt"]
+    assert (a["depth"][:5] == b["depth"][:5]).mean() > 0.97
+    assert np.abs(a["q"][:3] - b["q"][:3]).max() < 5e-3
+    ma, mb = a["q"][150:].mean(axis=(0, 1)), b["q"][150:].mean(axis=(0, 1))
+    sa, sb = a["q"][150:].std(axis=(0, 1)), b["q"][150:].std(axis=(0, 1))
+    assert np.abs(ma - mb).max() < 0.1 * sa.max() and np.allclose(sa, sb, rtol=0.1)
+    acc_a, acc_b = a["mean_tree_accept"][150:].mean(), b["mean_tree_accept"][150:].mean()
+    assert abs(acc_a - acc_b) < 0.02 and 0.7 < acc_a < 0.95
+    assert all(r.phase == _capi.PHASE_DONE for r in a["reports"])
