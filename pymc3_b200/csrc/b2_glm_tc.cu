@@ -8,7 +8,7 @@
 //
 // One CTA owns 128 chains (the MMA M dimension) and a contiguous range of 64-observation tiles.
 // Per tile, flash-attention style, with nothing but the X tile crossing HBM/L2:
-//   GEMM1  S[128 chains, 64 obs]   = Q . Xtile^T     tcgen05.mma SS, A = Q (smem), B = Xtile (smem, K-major)
+//   GEMM1  S[128 chains, 64 obs]   = Q . Xtile^T     tcgen05.mma TS, A = Q (TMEM, written once per CTA), B = Xtile (smem, K-major)
 //   epi    R = y - sigmoid(S), logp += ...           tcgen05.ld -> registers -> bf16 hi/lo -> tcgen05.st (TMEM)
 //   GEMM2  G[128 chains, 128 feat] += R . Xtile      tcgen05.mma TS, A = R (TMEM), B = the SAME smem tile, MN-major
 // fp32-level accuracy from bf16 tensor cores by two-term splits (x = hi + lo, both bf16):
@@ -22,18 +22,20 @@
 // always has four epilogue warps to interleave -- one warp per scheduler was latency-bound, ncu r1).
 #include <cuda_bf16.h>
 #include <cstring>
+#include <cstdlib>
 #include "b2_engine.cuh"
 
 #define TC_CHAINS 128                 // MMA M
 #define TC_OBS 64                     // observations per tile (GEMM1 N, GEMM2 K)
 #define TC_KP 128                     // padded feature count (GEMM1 K, GEMM2 N)
-#define TC_STAGES 4
+#define TC_STAGES 6
 #define TC_XPART_BYTES (TC_OBS * TC_KP * 2)            // 16384: one of {hi, lo}, two 64-column atoms
-#define TC_STAGE_DATA (2 * TC_XPART_BYTES + TC_OBS * 4) // 33024: Xhi | Xlo | y
-#define TC_STAGE_BYTES 33792                           // padded to a multiple of 1024
+#define TC_Y_BYTES (TC_OBS * 4)                        // 256
+#define TC_STAGE_DATA (2 * TC_XPART_BYTES + TC_Y_BYTES) // 33024 in global memory: Xhi | Xlo | y
+#define TC_STAGE_BYTES (2 * TC_XPART_BYTES)            // 32768 in shared memory (y lives in its own ring)
 #define TC_QPART_BYTES (TC_CHAINS * TC_KP * 2)         // 32768
 #define TC_Q_BYTES (2 * TC_QPART_BYTES)                // 65536
-#define TC_SMEM_BYTES (1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256)
+#define TC_SMEM_BYTES (1024 + TC_STAGES * (TC_STAGE_BYTES + TC_Y_BYTES) + 256)
 #define TC_EPI_GROUPS 4               // epilogue warpgroups; group g owns observation columns 16g..16g+15 of a tile
 #define TC_EPI_WARPS (4 * TC_EPI_GROUPS)
 #define TC_THREADS (128 + 32 * TC_EPI_WARPS)
@@ -41,6 +43,7 @@
 #define TC_COL_S 0                    // S[b] at 64 b
 #define TC_COL_P 128                  // P[b] at 128 + 64 b   (hi: 32 cols, lo: 32 cols; 2 bf16 per column)
 #define TC_COL_G 256                  // 128 columns
+#define TC_COL_Q 384                  // Q as the A operand of GEMM1: hi 64 cols | lo 64 cols (2 bf16 per column)
 
 struct TcWorkspace {
     unsigned char* xt;       // [n_tiles][TC_STAGE_DATA] pre-swizzled X tiles (+ y)
@@ -49,7 +52,12 @@ struct TcWorkspace {
     double* lpart;           // [splits][TC_EPI_GROUPS][c_pad]
     int n_tiles, c_pad, chain_tiles, splits, tiles_per_split, n_pad_rows;
     int* err;                // device watchdog flag
+    // per launch: where every chain's pending position lives
+    const float* qA; const float* qB; int ld; const B2ChainState* st; int n_chains; int K1;
+    long long* dbg;          // optional timeline of CTA (0,0): [event][tile] clock64 stamps (B2_TC_TIMELINE=1)
 };
+#define TC_DBG_TILES 256
+#define TC_STAMP(ev, t) do { if (ws.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (t) < TC_DBG_TILES) ws.dbg[(ev) * TC_DBG_TILES + (t)] = clock64(); } while (0)
 
 // byte offset of element (row, col) inside a [rows][64]-bf16 atom with the 128B swizzle
 // (Swizzle<3,4,3>: 16-byte chunk index ^= row % 8) -- the image TMA SWIZZLE_128B would produce.
@@ -132,9 +140,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
         }
     }
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -194,9 +214,9 @@ __device__ __forceinline__ float tc_rcp(float x) { float y; asm("rcp.approx.ftz.
 __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* q_s = smem;
-    unsigned char* x_s = smem + TC_Q_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + TC_STAGES * TC_STAGE_BYTES);
+    unsigned char* x_s = smem;
+    unsigned char* y_s = x_s + TC_STAGES * TC_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(y_s + TC_STAGES * TC_Y_BYTES);
     uint64_t* q_full = bars;                       // 1
     uint64_t* x_full = bars + 1;                   // TC_STAGES
     uint64_t* x_empty = x_full + TC_STAGES;        // TC_STAGES
@@ -214,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     const int T = t_end - t_begin;                 // >= 1 by construction of the grid
 
     if (warp == 1 && lane == 0) {
-        mbar_init(q_full, 1);
+        mbar_init(q_full, TC_EPI_WARPS);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TC_EPI_WARPS / 2); mbar_init(p_full + i, TC_EPI_WARPS / 2); mbar_init(p_empty + i, 1); }
         mbar_init(g_full, 1);
@@ -232,68 +252,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     if (warp == 0) {
         // ===== producer: Q tile once, then the X tile ring =====
         if (lane == 0) {
-            mbar_expect_tx(q_full, TC_Q_BYTES);
-            bulk_g2s(q_s, ws.qt + (size_t)ctile * TC_Q_BYTES, TC_Q_BYTES, q_full);
             for (int t = 0; t < T; ++t) {
                 const int s = t % TC_STAGES;
                 if (t >= TC_STAGES) mbar_wait(x_empty + s, ((t / TC_STAGES) - 1) & 1, ws.err, 1);
+                const unsigned char* src = ws.xt + (size_t)(t_begin + t) * TC_STAGE_DATA;
                 mbar_expect_tx(x_full + s, TC_STAGE_DATA);
-                bulk_g2s(x_s + s * TC_STAGE_BYTES, ws.xt + (size_t)(t_begin + t) * TC_STAGE_DATA, TC_STAGE_DATA, x_full + s);
+                bulk_g2s(x_s + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, x_full + s);
+                bulk_g2s(y_s + s * TC_Y_BYTES, src + TC_STAGE_BYTES, TC_Y_BYTES, x_full + s);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t q_addr = smem_u32(q_s);
-            mbar_wait(q_full, 0, ws.err, 2);
+        // ===== GEMM1 issuer.  The whole warp runs the (warp-uniform) loop so descriptors and TMEM
+        // addresses stay in uniform registers; only tcgen05.mma / tcgen05.commit are issued by one
+        // elected lane.  (Under `if (lane == 0)` ptxas wrapped every UTCHMMA in an R2UR + per-thread
+        // election loop: ~75 cycles of issue per MMA against 32-64 cycles of tensor work.)
+        // GEMM1 and GEMM2 have their own issuing warps (1 and 3): tcgen05.mma issue blocks on a shallow
+        // queue, so with a single issuer every barrier poll between the two GEMMs was tensor idle time
+        // (timeline r1: 2460 cycles of issuer time per tile for 1536 cycles of tensor work).
+        mbar_wait(q_full, 0, ws.err, 2);                           // epilogue warps have written Q into TMEM
+        tc_fence_after();
+        for (int t = 0; t < T; ++t) {
+            const int s = t % TC_STAGES, b = t & 1;
+            if (lane == 0) TC_STAMP(0, t);
+            mbar_wait(x_full + s, (t / TC_STAGES) & 1, ws.err, 3);
+            if (t >= 2) mbar_wait(s_empty + b, ((t >> 1) - 1) & 1, ws.err, 4);
             tc_fence_after();
-            for (int t = 0; t <= T; ++t) {
-                if (t < T) {
-                    const int s = t % TC_STAGES, b = t & 1;
-                    mbar_wait(x_full + s, (t / TC_STAGES) & 1, ws.err, 3);
-                    if (t >= 2) mbar_wait(s_empty + b, ((t >> 1) - 1) & 1, ws.err, 4);
-                    tc_fence_after();
-                    const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
-                    const uint32_t d = tmem + TC_COL_S + 64 * b;
-                    uint32_t acc = 0;
+            const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
+            const uint32_t d = tmem + TC_COL_S + 64 * b;
+            if (elect_one()) {
+                uint32_t acc = 0;
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {          // Qhi.Xhi, Qlo.Xhi, Qhi.Xlo
-                        const uint32_t qa = q_addr + (pass == 1 ? TC_QPART_BYTES : 0);
-                        const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
+                for (int pass = 0; pass < 3; ++pass) {              // Qhi.Xhi, Qlo.Xhi, Qhi.Xlo
+                    const uint32_t qa = tmem + TC_COL_Q + (pass == 1 ? 64 : 0);
+                    const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
 #pragma unroll
-                        for (int j = 0; j < TC_KP / 16; ++j) {
-                            const uint32_t koff = (j & 3) * 32;
-                            const uint64_t ad = make_desc(qa + (j >> 2) * (TC_CHAINS * 128) + koff, 16, 1024);
-                            const uint64_t bd = make_desc(xa + (j >> 2) * (TC_OBS * 128) + koff, 16, 1024);
-                            mma_ss(d, ad, bd, TC_IDESC_G1, acc);
-                            acc = 1;
-                        }
+                    for (int j = 0; j < TC_KP / 16; ++j) {
+                        const uint32_t koff = (j & 3) * 32;
+                        const uint64_t bd = make_desc(xa + (j >> 2) * (TC_OBS * 128) + koff, 16, 1024);
+                        mma_ts(d, qa + j * 8, bd, TC_IDESC_G1, acc);   // A from TMEM: no 4 KB smem read per MMA
+                        acc = 1;
                     }
-                    tc_commit(s_full + b);
                 }
-                if (t >= 1) {
-                    const int u = t - 1, s = u % TC_STAGES, b = u & 1;
-                    mbar_wait(p_full + b, (u >> 1) & 1, ws.err, 5);
-                    tc_fence_after();
-                    const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
-                    const uint32_t p_base = tmem + TC_COL_P + 64 * b;
-                    const uint32_t d = tmem + TC_COL_G;
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {          // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
-                        const uint32_t pa = p_base + (pass == 1 ? 32 : 0);
-                        const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
-#pragma unroll
-                        for (int j = 0; j < TC_OBS / 16; ++j) {
-                            // MN-major B: 2 feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
-                            const uint64_t bd = make_desc(xa + j * 2048, TC_OBS * 128, 1024);
-                            mma_ts(d, pa + j * 8, bd, TC_IDESC_G2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
-                        }
-                    }
-                    tc_commit(x_empty + s);
-                    tc_commit(p_empty + b);
-                    if (u == T - 1) tc_commit(g_full);
-                }
+                tc_commit(s_full + b);
+                TC_STAMP(1, t);
             }
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ===== GEMM2 issuer: G += R(u) . Xtile(u), three split passes; releases the X stage and the R buffer
+        for (int u = 0; u < T; ++u) {
+            const int s = u % TC_STAGES, b = u & 1;
+            if (lane == 0) TC_STAMP(2, u);
+            mbar_wait(p_full + b, (u >> 1) & 1, ws.err, 5);
+            tc_fence_after();
+            const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
+            const uint32_t p_base = tmem + TC_COL_P + 64 * b;
+            const uint32_t d = tmem + TC_COL_G;
+            if (elect_one()) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {              // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
+                    const uint32_t pa = p_base + (pass == 1 ? 32 : 0);
+                    const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
+#pragma unroll
+                    for (int j = 0; j < TC_OBS / 16; ++j) {
+                        // MN-major B: 2 feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
+                        const uint64_t bd = make_desc(xa + j * 2048, TC_OBS * 128, 1024);
+                        mma_ts(d, pa + j * 8, bd, TC_IDESC_G2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(x_empty + s);
+                tc_commit(p_empty + b);
+                if (u == T - 1) tc_commit(g_full);
+                TC_STAMP(3, u);
+            }
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue warpgroups: thread == (chain row, 16-observation column group) =====
@@ -304,13 +336,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
         // Column groups {0,1} take even tiles, {2,3} odd tiles (32 observation columns per warp and
         // tile): the two pairs run one tile apart, so MUFU-heavy math of one pair overlaps the TMEM
         // loads / stores / barrier waits of the other instead of all 16 warps marching in lock-step.
+        {   // Q (A operand of GEMM1): this thread's chain row, features 32cg..32cg+31, bf16 hi/lo split
+            const int chain = ctile * TC_CHAINS + row;
+            bool live = chain < ws.n_chains;
+            int sel = 0;
+            if (live && ws.st) { live = ws.st[chain].phase <= B2_PHASE_HMC; sel = ws.st[chain].sel; }
+            const float* q = (sel ? ws.qB : ws.qA) + (size_t)(live ? chain : 0) * ws.ld;
+            uint32_t qh[16], ql[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = 32 * cg + 2 * i;
+                const float a = (live && k < ws.K1) ? q[k] : 0.f;
+                const float b2 = (live && k + 1 < ws.K1) ? q[k + 1] : 0.f;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b2);
+                const float2 back = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - back.x, b2 - back.y);
+                qh[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                ql[i] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            TC_ST16(tmem + lane_addr + TC_COL_Q + 16 * cg, qh);
+            TC_ST16(tmem + lane_addr + TC_COL_Q + 64 + 16 * cg, ql);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_full);
+        }
         const int pair = cg >> 1, sub = cg & 1;
-        double logp = 0.0;
+        float lp_sum = 0.f, lp_comp = 0.f;                         // Kahan: no FP64 adds in the tile loop (ncu r1b)
         for (int t = pair; t < T; t += 2) {
             const int s = t % TC_STAGES, b = pair;
-            const float4* ys4 = reinterpret_cast<const float4*>(x_s + s * TC_STAGE_BYTES + 2 * TC_XPART_BYTES) + 8 * sub;
+            const float4* ys4 = reinterpret_cast<const float4*>(y_s + s * TC_Y_BYTES) + 8 * sub;
+            const bool stamp = (lane == 0) && (sub == 0) && (wq == 0);
+            if (stamp) TC_STAMP(4, t);
             mbar_wait(x_full + s, (t / TC_STAGES) & 1, ws.err, 9);    // y values of this stage (async-proxy writes)
             mbar_wait(s_full + b, (t >> 1) & 1, ws.err, 6);
+            if (stamp) TC_STAMP(5, t);
             tc_fence_after();
             uint32_t v[2][16];
             TC_LD16(tmem + lane_addr + TC_COL_S + 64 * b + 32 * sub, v[0]);
@@ -319,6 +379,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + b);                 // S(t) is in registers: GEMM1(t+2) may overwrite it
+            if (stamp) TC_STAMP(6, t);
+            if (lane == 0) TC_STAMP(9 + 2 * (warp - 4), t);
             uint32_t hi[2][8], lo[2][8];
             float lsum = 0.f;
 #pragma unroll
@@ -351,6 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
                     lo[hh][i] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
             }
+            if (stamp) TC_STAMP(7, t);
             if (t >= 2) mbar_wait(p_empty + b, ((t >> 1) - 1) & 1, ws.err, 7);
             tc_fence_after();
 #pragma unroll
@@ -362,8 +425,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full + b);
-            logp += (double)lsum;
+            if (stamp) TC_STAMP(8, t);
+            if (lane == 0) TC_STAMP(10 + 2 * (warp - 4), t);
+            const float ky = lsum - lp_comp;
+            const float kt = lp_sum + ky;
+            lp_comp = (kt - lp_sum) - ky;
+            lp_sum = kt;
         }
+        const double logp = (double)lp_sum - (double)lp_comp;
         // the slab's gradient tile: G[chain row][128 features] -> global partials (32 columns per group)
         mbar_wait(g_full, 0, ws.err, 8);
         tc_fence_after();
@@ -475,10 +544,8 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
     float* gr = w.V(B2_V_GE0 + s.sel, c);
     const double lp = tc_finalize_chain(ws, c, g.lane(), K1, prior_tau, q, gr);
     __syncwarp();
-    const bool active = b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
+    b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
     if (g.lane() == 0) w.st[c] = s;
-    __syncwarp();
-    if (active) tc_pack_chain(ws, c, g.lane(), K1, w.V(B2_V_QE0 + s.sel, c), true);
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -506,11 +573,15 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     w.tiles_per_split = (w.n_tiles + splits - 1) / splits;
     w.splits = (w.n_tiles + w.tiles_per_split - 1) / w.tiles_per_split;
     B2_CUDA_OK(cudaMalloc(&w.xt, (size_t)w.n_tiles * TC_STAGE_DATA));
-    B2_CUDA_OK(cudaMalloc(&w.qt, (size_t)w.chain_tiles * TC_Q_BYTES));
-    B2_CUDA_OK(cudaMemsetAsync(w.qt, 0, (size_t)w.chain_tiles * TC_Q_BYTES, stream));
+    w.qt = nullptr;
     B2_CUDA_OK(cudaMalloc(&w.gpart, (size_t)w.splits * w.c_pad * TC_KP * sizeof(float)));
     B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)w.splits * TC_EPI_GROUPS * w.c_pad * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&w.err, sizeof(int)));
+    w.dbg = nullptr;
+    if (getenv("B2_TC_TIMELINE")) {
+        B2_CUDA_OK(cudaMalloc(&w.dbg, 48 * TC_DBG_TILES * sizeof(long long)));
+        B2_CUDA_OK(cudaMemsetAsync(w.dbg, 0, 48 * TC_DBG_TILES * sizeof(long long), stream));
+    }
     B2_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), stream));
     k_glm_tc_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt, w.n_tiles);
     B2_CUDA_OK(cudaGetLastError());
@@ -524,7 +595,7 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
 void b2_glm_tc_release(b2_engine* e) {
     if (!e->glm_tc) return;
     TcHostState* hs = (TcHostState*)e->glm_tc;
-    cudaFree(hs->ws.xt); cudaFree(hs->ws.qt); cudaFree(hs->ws.gpart); cudaFree(hs->ws.lpart); cudaFree(hs->ws.err);
+    cudaFree(hs->ws.dbg); cudaFree(hs->ws.xt); cudaFree(hs->ws.qt); cudaFree(hs->ws.gpart); cudaFree(hs->ws.lpart); cudaFree(hs->ws.err);
     delete hs;
     e->glm_tc = nullptr;
 }
@@ -535,12 +606,12 @@ static int tc_ensure(b2_engine* e, cudaStream_t stream) {
 }
 
 int b2_glm_tc_pack(b2_engine* e, const float* qA, const float* qB, int ld, const B2ChainState* st, int n, cudaStream_t stream) {
+    // positions are split to bf16 hi/lo inside k_glm_tc_main (written straight into TMEM); only the
+    // one-time X tiling has to exist before the first launch
     int rc = tc_ensure(e, stream);
     if (rc) return rc;
     TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
-    k_glm_tc_pack_q<<<dim3(w.chain_tiles, 16), 256, 0, stream>>>(qA, qB, ld, st, n, e->md.G + 1, w.qt);
-    B2_CUDA_OK(cudaGetLastError());
-    e->launches += 1;
+    w.qA = qA; w.qB = qB; w.ld = ld; w.st = st; w.n_chains = n; w.K1 = e->md.G + 1;
     return 0;
 }
 
@@ -548,6 +619,16 @@ int b2_glm_tc_main(b2_engine* e, cudaStream_t stream) {
     TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
     k_glm_tc_main<<<dim3(w.chain_tiles, w.splits), TC_THREADS, TC_SMEM_BYTES, stream>>>(w);
     e->launches += 1;
+    return 0;
+}
+
+// debugging aid: copies the clock64 timeline of CTA (0,0) to the host (9 events x TC_DBG_TILES)
+extern "C" int b2_debug_tc_timeline(b2_engine* e, long long* host_out) {
+    if (!e || !e->glm_tc) return -1;
+    TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
+    if (!w.dbg) return -2;
+    B2_CUDA_OK(cudaDeviceSynchronize());
+    B2_CUDA_OK(cudaMemcpy(host_out, w.dbg, 48 * TC_DBG_TILES * sizeof(long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 
