@@ -330,12 +330,17 @@ def run_b200(args):
 
     peaks = measured_peaks()
     roofline = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if args.workload == "c2" and os.path.exists(tpath):        # one ncu --set full capture, per launch
+        with open(tpath) as f:
+            traffic = json.load(f).get("k_glm_tc_main", {}).get("dram_bytes_per_launch")
     if like_n > 0 and wl["bound"]:
         per_launch_s = like_ms / 1e3 / like_n
         if wl["bound"] == "tensor":
             ach = wl["flops_per_chain_grad"] * chains / per_launch_s / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tflops"], "traffic": None}
+                        "frac": ach / peaks["tflops"], "traffic": traffic}
         else:
             ach = wl["bytes_per_chain_grad"] * chains / per_launch_s / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -307,8 +307,8 @@ B2_HD int b2_begin_transition(const G& g, const B2View<T>& w, int c, B2ChainStat
     double kin[1] = {0.0};
     for (int i = g.lane(); i < w.D; i += G::NT) {
         // quadpotential.py:200-203: inv_stds * normal,  inv_stds = 1 / sqrt(var)
-        const T inv_std = (T)1 / (T)sqrt((double)var[i]);
-        const T p = inv_std * (T)b2_normal(s.key0, s.key1, t, (uint32_t)i);
+        const T inv_std = (T)1 / (T)sqrt(var[i]);
+        const T p = inv_std * B2Normal<T>::draw(s.key0, s.key1, t, (uint32_t)i);
         const T qq = pq[i], gg = pg[i];
         q1[i] = qq; p1[i] = p; g1[i] = gg;
         if (nuts) { q0[i] = qq; p0[i] = p; g0[i] = gg; ps[i] = p; }

@@ -68,3 +68,23 @@ B2_HD double b2_normal(uint32_t k0, uint32_t k1, uint32_t t, uint32_t i) {
     double ang = 6.283185307179586476925286766559 * u2;
     return rad * ((i & 1u) ? sin(ang) : cos(ang));
 }
+
+// Same stream, element type T: the fp32 production build does the Box-Muller transcendentals in float
+// (double log/sqrt/sincos per momentum component dominated the transition-ending path of the lock-step
+// advance kernel); the uniforms are the same 53-bit values, so fp32 and fp64 builds draw the same
+// normals to ~1e-7.
+template <typename T> struct B2Normal;
+template <> struct B2Normal<double> {
+    B2_HD static double draw(uint32_t k0, uint32_t k1, uint32_t t, uint32_t i) { return b2_normal(k0, k1, t, i); }
+};
+template <> struct B2Normal<float> {
+    B2_HD static float draw(uint32_t k0, uint32_t k1, uint32_t t, uint32_t i) {
+        uint32_t r[4];
+        b2_philox4x32_10(t, B2_PURPOSE_MOMENTUM, i >> 1, 0u, k0, k1, r);
+        const float u1 = (float)(1.0 - b2_u53(r[0], r[1]));     // (0, 1]
+        const float u2 = (float)b2_u53(r[2], r[3]);
+        const float rad = sqrtf(-2.0f * logf(u1 > 1e-37f ? u1 : 1e-37f));
+        const float ang = 6.2831853071795864f * u2;
+        return rad * ((i & 1u) ? sinf(ang) : cosf(ang));
+    }
+};
