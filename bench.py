@@ -383,6 +383,91 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """Config 5: logistic regression with the OBSERVATIONS sharded over the GPUs (weak scaling in rows:
+    6.25 M rows x 256 features per GPU = 50 M rows on 8), every rank runs all 256 chains redundantly and
+    the ranks all-reduce the packed [C, D+1] (logp, dlogp) partials once per leapfrog over NCCL."""
+    import torch
+    import torch.distributed as dist
+    from pymc3_b200 import _capi
+    from pymc3_b200.model import LogisticGLM
+    from pymc3_b200.sharded import run_lockstep_sharded
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    rows = args.n_obs or 6250000
+    k = args.n_features or 256
+    chains = args.chains or 256
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5000 + rank)                                 # shard-keyed stream (SURVEY 8d, C5)
+    X = torch.randn((rows, k), generator=gen, device=dev, dtype=torch.float32).bfloat16().float()
+    beta = torch.as_tensor(np.random.default_rng(5).normal(0, 0.5 / np.sqrt(k / 100.0), size=k), dtype=torch.float32, device=dev)
+    y = (torch.rand(rows, generator=gen, device=dev) < torch.sigmoid(0.3 + X @ beta)).float()
+    model = LogisticGLM(X, y)
+    ndim = k + 1
+    ips, K, W = args.iters_per_step, args.steps, args.warmup
+    total = (K + W) * ips
+    tune = total // 2
+    eng = model.engine(chains, dtype=args.dtype, device=local_rank)
+    eng.set_state(start_points(ndim, chains, 0) * 0.1, chain_seeds(chains, 0), 0.25 / ndim ** 0.25, np.zeros(ndim),
+                  np.ones(ndim), 10.0)
+    opts = dict(max_treedepth=10, early_max_treedepth=8, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75, t0=10.0,
+                adapt_step_size=1, adapt_mass=1, path_length=2.0, max_steps=1024, hmc_jitter=0,
+                exec_mode=_capi.B2_EXEC_LOCKSTEP, glm_path={"auto": 0, "group": 1, "simt": 2, "tcgen05": 3}[args.glm_path])
+    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    trace = eng.alloc_trace(_capi.B2_NUTS, total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for s in range(W):
+        run_lockstep_sharded(eng, _capi.B2_NUTS, ips, tune, opts, allreduce, world, out=trace, row0=s * ips)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.kernel_launches()
+    ev0.record()
+    steps = 0
+    for s in range(K):
+        run_lockstep_sharded(eng, _capi.B2_NUTS, ips, tune, opts, allreduce, world, out=trace, row0=(W + s) * ips)
+        steps += eng.last_lockstep_steps
+    ev1.record()
+    barrier()
+    t_local = ev0.elapsed_time(ev1) / 1e3
+    t_all = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    t_timed = float(t_all.item())
+    leap = int(trace["tree_size"][W * ips:].sum().item())          # replicated chains: count them once
+    launches = eng.kernel_launches() - launches0
+    if rank == 0:
+        peaks = measured_peaks()
+        per_step = t_timed / max(steps, 1)
+        x_bytes = rows * k * 4.0
+        flops = 4.0 * rows * (k + 1) * chains
+        line = {"metric": "leapfrog_grad_evals_per_sec", "value": leap / t_timed, "unit": "grad-evals/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": t_timed * 1e3 / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+                "config": {"workload": "logistic regression, observations sharded: %d rows x %d features per GPU, %d rows total"
+                           % (rows, k, rows * world), "chains": chains, "iters_per_step": ips, "tune": tune, "draws": total - tune,
+                           "collective": "all-reduce(sum) of [C, D+1] fp64 = %d bytes per leapfrog" % (chains * (k + 1) * 8)},
+                "lockstep_steps_timed": steps, "ms_per_leapfrog_all_chains": per_step * 1e3, "gpu_launches": launches,
+                "e2e": None,
+                "roofline": {"bound": "hbm", "achieved": x_bytes / per_step / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": x_bytes / per_step / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                             "tensor_achieved_tflops": flops / per_step / 1e12, "tensor_frac": flops / per_step / 1e12 / peaks["tflops"],
+                             "note": "per GPU, whole lock-step step (likelihood + all-reduce + advance); bytes = X shard read once"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -410,7 +495,7 @@ def main():
     ap.add_argument("--steps", type=int, default=17)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--iters-per-step", type=int, default=100)
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--n-obs", type=int, default=0)
@@ -429,6 +514,8 @@ def main():
         args.warmup = 3                      # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_b200(args)
 

@@ -141,6 +141,21 @@ int b2_set_position(b2_engine* e, const void* d_q, void* stream);
  * chains at once: BaseHMC.astep + NUTS/HamiltonianMC._hamiltonian_step + adaptation + record. */
 int b2_sample_run(b2_engine* e, const b2_sampler_opts* opts, const b2_trace_out* trace, void* stream);
 
+/* Stepwise form of b2_sample_run for the observation-sharded configuration (BASELINE.json config 5,
+ * SURVEY 8e): the reference has no counterpart (it never shards a likelihood); the seam is the same
+ * ValueGradFunction.__call__ (model.py:645-666) whose result becomes a sum over ranks.  Every rank
+ * holds a row shard of the data and ALL chains; per leapfrog
+ *     b2_step_likelihood  -> d_packed[C, D+1] fp64 = (partial logp, partial dlogp) of each pending position
+ *     all-reduce(sum) of d_packed over ranks (NCCL; done by the caller)
+ *     b2_step_advance     -> unpacks the reduced values (prior counted once: pass prior_copies = world
+ *                            size) and advances every chain's NUTS/HMC state machine by one leapfrog.
+ * b2_step_active returns how many chains still need gradients; b2_step_end closes the run. */
+int b2_step_begin(b2_engine* e, const b2_sampler_opts* opts, const b2_trace_out* trace, void* stream);
+int b2_step_likelihood(b2_engine* e, double* d_packed, void* stream);
+int b2_step_advance(b2_engine* e, const double* d_packed, int32_t prior_copies, void* stream);
+int b2_step_active(b2_engine* e, int32_t* host_count, void* stream);
+int b2_step_end(b2_engine* e);
+
 /* adaptation / bookkeeping state back to the host (step.step_size, potential._var, warnings) */
 int b2_get_chain_reports(b2_engine* e, b2_chain_report* host_out /* [C] */);
 int b2_get_mass_var(b2_engine* e, double* host_out /* [C, D] */);

@@ -366,7 +366,7 @@ static bool persistent_ok(const b2_engine* e) {
 }
 
 template <typename T>
-static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr, cudaStream_t s) {
+static B2View<T> build_view(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr) {
     B2View<T> w = make_view<T>(e);
     w.kind = o->kind;
     w.iter_base = e->iter_done; w.iter_end = e->iter_done + o->n_iters; w.tune_until = o->tune_until;
@@ -381,6 +381,12 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         w.tr_accept = tr->d_accept; w.tr_depth = tr->d_depth; w.tr_tree_size = tr->d_tree_size; w.tr_n_steps = tr->d_n_steps;
         w.tr_diverging = tr->d_diverging; w.tr_tune = tr->d_tune; w.tr_accepted = tr->d_accepted;
     }
+    return w;
+}
+
+template <typename T>
+static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr, cudaStream_t s) {
+    B2View<T> w = build_view<T>(e, o, tr);
     int mode = o->exec_mode;
     if (mode == B2_EXEC_AUTO) mode = persistent_ok(e) ? B2_EXEC_PERSISTENT : B2_EXEC_LOCKSTEP;
     if (mode == B2_EXEC_PERSISTENT && e->md.family == B2_FAMILY_GLM_LOGIT) {
@@ -460,6 +466,141 @@ extern "C" int b2_sample_run(b2_engine* e, const b2_sampler_opts* o, const b2_tr
     B2_CUDA_OK(cudaSetDevice(e->device));
     return e->dtype == B2_F64 ? run_t<double>(e, o, trace, (cudaStream_t)stream)
                               : run_t<float>(e, o, trace, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- stepwise lock-step API
+// For the observation-sharded configuration: every rank runs every chain's state
+// machine redundantly on its own rows; the host interleaves a collective between the two halves of
+// a leapfrog:  b2_step_likelihood -> all-reduce(packed [C, D+1] fp64) -> b2_step_advance.
+template <typename T>
+__global__ void k_pack_eval(B2View<T> w, double* __restrict__ packed) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= w.C) return;
+    double* row = packed + (size_t)c * (w.D + 1);
+    const B2ChainState& s = w.st[c];
+    if (!b2_needs_grad(s.phase)) {                 // keep the collective's payload finite for idle chains
+        for (int i = lane; i <= w.D; i += 32) row[i] = 0.0;
+        return;
+    }
+    const T* g = w.V(B2_V_GE0 + s.sel, c);
+    if (lane == 0) row[0] = w.logp_eval[c];
+    for (int i = lane; i < w.D; i += 32) row[1 + i] = (double)g[i];
+}
+
+// unpack the reduced values; for the GLM family remove the (world - 1) surplus copies of the prior that
+// every rank added to its partial (prior_copies = world_size)
+template <typename T>
+__global__ void k_unpack_eval(B2View<T> w, const double* __restrict__ packed, int family, double prior_tau, int prior_copies) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= w.C) return;
+    const B2ChainState& s = w.st[c];
+    if (!b2_needs_grad(s.phase)) return;
+    const double* row = packed + (size_t)c * (w.D + 1);
+    const T* q = w.V(B2_V_QE0 + s.sel, c);
+    T* g = w.V(B2_V_GE0 + s.sel, c);
+    const double extra = (double)(prior_copies - 1);
+    double prior = 0.0;
+    for (int i = lane; i < w.D; i += 32) {
+        double gi = row[1 + i];
+        if (family == B2_FAMILY_GLM_LOGIT && i > 0 && extra > 0) {
+            const double b = (double)q[i];
+            gi += extra * prior_tau * b;
+            prior += 0.5 * (-prior_tau * b * b + log(prior_tau) - B2_LOG_2PI);
+        }
+        g[i] = (T)gi;
+    }
+    for (int o = 16; o > 0; o >>= 1) prior += __shfl_xor_sync(0xffffffffu, prior, o);
+    if (lane == 0) w.logp_eval[c] = row[0] - extra * prior;
+}
+
+template <typename T>
+static int step_likelihood_t(b2_engine* e, double* d_packed, cudaStream_t s) {
+    B2View<T> w = build_view<T>(e, &e->step_opts, &e->step_trace);
+    const T* qA = w.V(B2_V_QE0, 0); const T* qB = w.V(B2_V_QE1, 0);
+    T* gA = w.V(B2_V_GE0, 0); T* gB = w.V(B2_V_GE1, 0);
+    int rc = launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, e->step_opts.glm_path, s);
+    if (rc) return rc;
+    k_pack_eval<T><<<(e->C + 3) / 4, 128, 0, s>>>(w, d_packed);
+    e->launches += 1;
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int step_advance_t(b2_engine* e, const double* d_packed, int prior_copies, cudaStream_t s) {
+    B2View<T> w = build_view<T>(e, &e->step_opts, &e->step_trace);
+    const int nb = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
+    k_unpack_eval<T><<<(e->C + 3) / 4, 128, 0, s>>>(w, d_packed, e->md.family, e->md.hp[0], prior_copies);
+    if (use_block_group(e)) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 0);
+    else k_advance_warp<T><<<nb, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 0);
+    e->launches += 2;
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2_step_begin(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* trace, void* stream) {
+    if (!e || !o) { b2_set_error("b2_step_begin: null argument"); return -1; }
+    if (!e->state_set) { b2_set_error("b2_step_begin: call b2_set_state first"); return -2; }
+    if (o->n_iters <= 0) { b2_set_error("b2_step_begin: n_iters must be > 0"); return -3; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    e->step_opts = *o;
+    memset(&e->step_trace, 0, sizeof(e->step_trace));
+    if (trace) e->step_trace = *trace;
+    e->stepping = true;
+    if (e->iter_done > 0) {                           // re-activate chains that finished the previous run
+        cudaStream_t s = (cudaStream_t)stream;
+        const int nb = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
+        if (e->dtype == B2_F64) {
+            B2View<double> w = build_view<double>(e, o, trace);
+            if (use_block_group(e)) k_advance_block<double><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 1);
+            else k_advance_warp<double><<<nb, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 1);
+        } else {
+            B2View<float> w = build_view<float>(e, o, trace);
+            if (use_block_group(e)) k_advance_block<float><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 1);
+            else k_advance_warp<float><<<nb, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 1);
+        }
+        e->launches += 1;
+        B2_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int b2_step_likelihood(b2_engine* e, double* d_packed, void* stream) {
+    if (!e || !d_packed || !e->stepping) { b2_set_error("b2_step_likelihood: call b2_step_begin first"); return -1; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    return e->dtype == B2_F64 ? step_likelihood_t<double>(e, d_packed, (cudaStream_t)stream)
+                              : step_likelihood_t<float>(e, d_packed, (cudaStream_t)stream);
+}
+
+extern "C" int b2_step_advance(b2_engine* e, const double* d_packed, int32_t prior_copies, void* stream) {
+    if (!e || !d_packed || !e->stepping) { b2_set_error("b2_step_advance: call b2_step_begin first"); return -1; }
+    if (prior_copies < 1) { b2_set_error("b2_step_advance: prior_copies must be >= 1"); return -2; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    return e->dtype == B2_F64 ? step_advance_t<double>(e, d_packed, prior_copies, (cudaStream_t)stream)
+                              : step_advance_t<float>(e, d_packed, prior_copies, (cudaStream_t)stream);
+}
+
+// number of chains that still need gradient evaluations (synchronises the stream)
+extern "C" int b2_step_active(b2_engine* e, int32_t* host_count, void* stream) {
+    if (!e || !host_count) { b2_set_error("b2_step_active: null argument"); return -1; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    B2_CUDA_OK(cudaMemsetAsync(e->d_active, 0, sizeof(int), s));
+    k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, e->d_active);
+    e->launches += 1;
+    B2_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(cudaStreamSynchronize(s));
+    *host_count = *e->h_active;
+    return 0;
+}
+
+extern "C" int b2_step_end(b2_engine* e) {
+    if (!e || !e->stepping) { b2_set_error("b2_step_end: no stepwise run in progress"); return -1; }
+    e->iter_done += e->step_opts.n_iters;
+    e->stepping = false;
+    return 0;
 }
 
 extern "C" int b2_get_chain_reports(b2_engine* e, b2_chain_report* out) {

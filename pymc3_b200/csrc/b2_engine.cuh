@@ -27,6 +27,10 @@ struct b2_engine {
     bool state_set;
     int64_t launches;
     int sm_count;
+    // stepwise lock-step run (observation sharding): options / trace of the run in progress
+    b2_sampler_opts step_opts;
+    b2_trace_out step_trace;
+    bool stepping;
     // optional live timing of the likelihood launches (bench.py roofline)
     int profile;
     double like_ms;

@@ -52,7 +52,12 @@ class Engine:
 
     # -- plumbing
     def _upload(self, array, dtype):
-        t = self.torch.as_tensor(np.ascontiguousarray(array, dtype=dtype), device=self.dev)
+        torch = self.torch
+        if isinstance(array, torch.Tensor):            # data generated on the device stays there
+            tdt = {"f4": torch.float32, "f8": torch.float64, np.uint8: torch.uint8, np.int32: torch.int32}[dtype]
+            t = array.to(device=self.dev, dtype=tdt).contiguous()
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(array, dtype=dtype), device=self.dev)
         self._keep.append(t)
         return t.data_ptr()
 

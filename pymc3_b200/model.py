@@ -248,8 +248,11 @@ class LogisticGLM(Model):
     family = _capi.B2_GLM_LOGIT
 
     def __init__(self, X, y, labels=None, prior_tau=1e-6):
-        self.X = np.ascontiguousarray(X, dtype="f4")
-        self.y = np.ascontiguousarray(y, dtype="f4")
+        if type(X).__module__.startswith("torch"):     # device-resident data (large, generated on the GPU)
+            self.X, self.y = X, y
+        else:
+            self.X = np.ascontiguousarray(X, dtype="f4")
+            self.y = np.ascontiguousarray(y, dtype="f4")
         if self.y.ndim > 1:
             raise TypeError("Only one-dimensional observed variable objects (i.e. of shape `(n, )`) "
                             "are supported")                       # glm/linear.py:55-58

@@ -287,3 +287,64 @@ def test_fused_tensor_core_lockstep_agrees_with_simt_lockstep():
     acc_a, acc_b = a["mean_tree_accept"][150:].mean(), b["mean_tree_accept"][150:].mean()
     assert abs(acc_a - acc_b) < 0.02 and 0.7 < acc_a < 0.95
     assert all(r.phase == _capi.PHASE_DONE for r in a["reports"])
+
+
+def test_stepwise_and_observation_sharded_runs_match_the_plain_run():
+    """SURVEY 8e (C5): (a) the stepwise API with one rank reproduces b2_sample_run bit for bit;
+    (b) two row shards on one GPU, their packed (logp, dlogp) summed as the all-reduce would, give the
+    same chains as the unsharded engine (fp64, to summation-order round-off)."""
+    import torch
+    from pymc3_b200 import model as pm
+    from pymc3_b200.sharded import row_shard, run_lockstep_sharded
+    import ctypes as C
+    X, y = models_util.glm_data(3000, 12, seed=21)
+    D, Cn, n, tune = 13, 6, 60, 40
+    rng = np.random.default_rng(5)
+    q0 = rng.uniform(-0.3, 0.3, size=(Cn, D))
+    seeds = np.arange(Cn) + 77
+    opts = dict(NUTS_OPTS)
+    opts["exec_mode"] = _capi.B2_EXEC_LOCKSTEP
+    opts["glm_path"] = _capi.B2_GLM_SIMT
+    opts["adapt_step_size"] = 0
+    ref = _run_engine(pm.LogisticGLM(X, y), q0, seeds, n, tune, _capi.B2_NUTS, "float64", _capi.B2_EXEC_LOCKSTEP,
+                      glm_path=_capi.B2_GLM_SIMT, adapt_step_size=0)
+    # (a) one rank, stepwise
+    eng = pm.LogisticGLM(X, y).engine(Cn, dtype="float64")
+    eng.set_state(q0, seeds, 0.25 / D ** 0.25, np.zeros(D), np.ones(D), 10.0)
+    one = run_lockstep_sharded(eng, _capi.B2_NUTS, n, tune, opts, None, 1)
+    assert np.array_equal(one["q"].cpu().numpy(), ref["q"]) and np.array_equal(one["depth"].cpu().numpy(), ref["depth"])
+    eng.close()
+    # (b) two shards, all-reduce emulated by adding the two packed buffers
+    engs = []
+    for r in range(2):
+        lo, hi = row_shard(len(y), 2, r)
+        e = pm.LogisticGLM(X[lo:hi], y[lo:hi]).engine(Cn, dtype="float64")
+        e.set_state(q0, seeds, 0.25 / D ** 0.25, np.zeros(D), np.ones(D), 10.0)
+        engs.append(e)
+    lib = engs[0].lib
+    traces = [e.alloc_trace(_capi.B2_NUTS, n) for e in engs]
+    packed = [torch.zeros((Cn, D + 1), dtype=torch.float64, device="cuda") for _ in engs]
+    o = _capi.SamplerOpts(kind=_capi.B2_NUTS, n_iters=n, tune_until=tune, **opts)
+    for e, tr_ in zip(engs, traces):
+        tr = _capi.TraceOut()
+        for name, t in tr_.items():
+            setattr(tr, "d_" + name, t.data_ptr())
+        _capi.check(lib.b2_step_begin(e.handle, C.byref(o), C.byref(tr), e._stream()), lib)
+    active = C.c_int32(1)
+    while active.value:
+        for _ in range(8):
+            for e, p in zip(engs, packed):
+                _capi.check(lib.b2_step_likelihood(e.handle, p.data_ptr(), e._stream()), lib)
+            total = packed[0] + packed[1]
+            for e, p in zip(engs, packed):
+                p.copy_(total)
+                _capi.check(lib.b2_step_advance(e.handle, p.data_ptr(), 2, e._stream()), lib)
+        _capi.check(lib.b2_step_active(engs[0].handle, C.byref(active), engs[0]._stream()), lib)
+    a, b = traces[0]["q"].cpu().numpy(), traces[1]["q"].cpu().numpy()
+    assert np.array_equal(a, b)                                       # replicated state machines stay identical
+    assert (traces[0]["depth"].cpu().numpy() == ref["depth"]).all()
+    assert np.abs(a - ref["q"]).max() < 1e-8
+    assert np.abs(traces[0]["model_logp"].cpu().numpy() - ref["model_logp"]).max() < 1e-6
+    for e in engs:
+        lib.b2_step_end(e.handle)
+        e.close()
