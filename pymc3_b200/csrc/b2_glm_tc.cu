@@ -13,9 +13,10 @@
 //   GEMM2  G[128 chains, 128 feat] += R . Xtile      tcgen05.mma TS, A = R (TMEM), B = the SAME smem tile, MN-major
 // fp32-level accuracy from bf16 tensor cores by two-term splits (x = hi + lo, both bf16):
 //   S = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo ,   G = Rhi.Xhi + Rlo.Xhi + Rhi.Xlo      (error ~2^-17 per product)
-// Operands are staged by cp.async.bulk (TMA engine, 1-D bulk copies): X is pre-tiled ONCE at model
+// X tiles are staged by cp.async.bulk (TMA engine, 1-D bulk copies): X is pre-tiled ONCE at model
 // build into the exact 128B-swizzled shared-memory image the UMMA descriptors expect, so a pipeline
-// stage is one contiguous 33 KB copy and no tensor map is needed.  Accumulators live in TMEM
+// stage is one contiguous 32 KB copy (+256 B of y) and no tensor map is needed.  Q (the positions) is
+// split to bf16 hi/lo by the epilogue warps and written straight into TMEM.  Accumulators live in TMEM
 // (S double-buffered 2x64 cols, R 2x64 cols, G 128 cols).  Warp roles: 0 = bulk-copy producer,
 // 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..19 = four epilogue warpgroups (TMEM lane ==
 // chain; warpgroup g takes observation columns 16g..16g+15 of every tile, so each SM sub-partition
@@ -33,8 +34,6 @@
 #define TC_Y_BYTES (TC_OBS * 4)                        // 256
 #define TC_STAGE_DATA (2 * TC_XPART_BYTES + TC_Y_BYTES) // 33024 in global memory: Xhi | Xlo | y
 #define TC_STAGE_BYTES (2 * TC_XPART_BYTES)            // 32768 in shared memory (y lives in its own ring)
-#define TC_QPART_BYTES (TC_CHAINS * TC_KP * 2)         // 32768
-#define TC_Q_BYTES (2 * TC_QPART_BYTES)                // 65536
 #define TC_SMEM_BYTES (1024 + TC_STAGES * (TC_STAGE_BYTES + TC_Y_BYTES) + 256)
 #define TC_EPI_GROUPS 4               // epilogue warpgroups; group g owns observation columns 16g..16g+15 of a tile
 #define TC_EPI_WARPS (4 * TC_EPI_GROUPS)
@@ -47,7 +46,6 @@
 
 struct TcWorkspace {
     unsigned char* xt;       // [n_tiles][TC_STAGE_DATA] pre-swizzled X tiles (+ y)
-    unsigned char* qt;       // [chain_tiles][TC_Q_BYTES] swizzled Q tiles, rewritten every launch
     float* gpart;            // [splits][c_pad][TC_KP]
     double* lpart;           // [splits][TC_EPI_GROUPS][c_pad]
     int n_tiles, c_pad, chain_tiles, splits, tiles_per_split, n_pad_rows;
@@ -87,29 +85,6 @@ __global__ void k_glm_tc_prep_x(const float* __restrict__ X, const float* __rest
     for (int r = threadIdx.x; r < TC_OBS; r += blockDim.x) {
         const int row = tile * TC_OBS + r;
         reinterpret_cast<float*>(blob + 2 * TC_XPART_BYTES)[r] = row < N ? y[row] : 0.f;
-    }
-}
-
-// ------------------------------------------------------- per-launch split of the positions
-__global__ void k_glm_tc_pack_q(const float* qA, const float* qB, int ld, const B2ChainState* st, int n_chains,
-                                int K1, unsigned char* __restrict__ qt) {
-    const int ctile = blockIdx.x;
-    unsigned char* blob = qt + (size_t)ctile * TC_Q_BYTES;
-    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < TC_CHAINS * TC_KP; idx += gridDim.y * blockDim.x) {
-        const int r = idx / TC_KP, c = idx - r * TC_KP;
-        const int chain = ctile * TC_CHAINS + r;
-        float v = 0.f;
-        if (chain < n_chains && c < K1) {
-            int sel = 0;
-            bool live = true;
-            if (st) { live = st[chain].phase <= B2_PHASE_HMC; sel = st[chain].sel; }
-            if (live) v = (sel ? qB : qA)[(size_t)chain * ld + c];
-        }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        const int off = (c >> 6) * (TC_CHAINS * 128) + tc_swz(r, c & 63);
-        *reinterpret_cast<__nv_bfloat16*>(blob + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(blob + TC_QPART_BYTES + off) = lo;
     }
 }
 
@@ -496,24 +471,6 @@ __device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int c
     return lp + prior + (double)ws.n_pad_rows * B2_LOG_2;
 }
 
-// bf16 hi/lo split of one chain's position into its row of the swizzled Q tile (lane l: features 4l..4l+3)
-__device__ __forceinline__ void tc_pack_chain(const TcWorkspace& ws, int chain, int lane, int K1, const float* q, bool live) {
-    unsigned char* blob = ws.qt + (size_t)(chain / TC_CHAINS) * TC_Q_BYTES;
-    const int r = chain % TC_CHAINS;
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = 4 * lane + j;
-        const float v = (live && c < K1) ? q[c] : 0.f;
-        hi[j] = __float2bfloat16_rn(v);
-        lo[j] = __float2bfloat16_rn(v - __bfloat162float(hi[j]));
-    }
-    const int c0 = 4 * lane;                   // 4 consecutive columns stay inside one 16-byte swizzle chunk
-    const int off = (c0 >> 6) * (TC_CHAINS * 128) + tc_swz(r, c0 & 63);
-    *reinterpret_cast<uint2*>(blob + off) = *reinterpret_cast<const uint2*>(hi);
-    *reinterpret_cast<uint2*>(blob + TC_QPART_BYTES + off) = *reinterpret_cast<const uint2*>(lo);
-}
-
 __global__ void k_glm_tc_finalize(TcWorkspace ws, int n_chains, int K1, double prior_tau, const float* qA,
                                   const float* qB, float* gA, float* gB, int ld, const B2ChainState* st, double* logp) {
     const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -573,7 +530,6 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     w.tiles_per_split = (w.n_tiles + splits - 1) / splits;
     w.splits = (w.n_tiles + w.tiles_per_split - 1) / w.tiles_per_split;
     B2_CUDA_OK(cudaMalloc(&w.xt, (size_t)w.n_tiles * TC_STAGE_DATA));
-    w.qt = nullptr;
     B2_CUDA_OK(cudaMalloc(&w.gpart, (size_t)w.splits * w.c_pad * TC_KP * sizeof(float)));
     B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)w.splits * TC_EPI_GROUPS * w.c_pad * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&w.err, sizeof(int)));
@@ -595,7 +551,7 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
 void b2_glm_tc_release(b2_engine* e) {
     if (!e->glm_tc) return;
     TcHostState* hs = (TcHostState*)e->glm_tc;
-    cudaFree(hs->ws.dbg); cudaFree(hs->ws.xt); cudaFree(hs->ws.qt); cudaFree(hs->ws.gpart); cudaFree(hs->ws.lpart); cudaFree(hs->ws.err);
+    cudaFree(hs->ws.dbg); cudaFree(hs->ws.xt); cudaFree(hs->ws.gpart); cudaFree(hs->ws.lpart); cudaFree(hs->ws.err);
     delete hs;
     e->glm_tc = nullptr;
 }

@@ -21,8 +21,8 @@ __global__ void __launch_bounds__(HT_CHAINS)
 k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, const int* __restrict__ grp_off,
             int N, int NG, const T* qA, const T* qB, int ld, const B2ChainState* st, int n_chains,
             int rows_per_split, T* __restrict__ part /* [split][2*NG+1][n_chains] */) {
-    __shared__ float ys[HT_TILE];
-    __shared__ unsigned char fs[HT_TILE];
+    __shared__ __align__(16) float ys[HT_TILE];
+    __shared__ __align__(16) float fs[HT_TILE];     // covariate converted u8 -> float once per tile, not per (chain, obs)
     __shared__ int s_g0;
     const int tid = threadIdx.x;
     const int chain = blockIdx.x * HT_CHAINS + tid;
@@ -50,12 +50,30 @@ k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, c
     for (int t0 = row_begin; t0 < row_end; t0 += HT_TILE) {
         const int cnt = min(HT_TILE, row_end - t0);
         __syncthreads();
-        for (int i = tid; i < cnt; i += HT_CHAINS) { ys[i] = y[t0 + i]; fs[i] = fl[t0 + i]; }
+        for (int i = tid; i < cnt; i += HT_CHAINS) { ys[i] = y[t0 + i]; fs[i] = (float)fl[t0 + i]; }
         __syncthreads();
         int i = 0;
         while (i < cnt) {
             const int stop = min(cnt, g_end - t0);      // block-uniform
             if (i < stop) dirty = true;
+            // scalar head up to a 4-aligned index, then 4 observations per shared-memory transaction
+            // (one LDS.128 of y + one LDS.128 of the covariate, both broadcast to the warp)
+            for (; i < stop && (i & 3); ++i) {
+                const T f = (T)fs[i];
+                const T r = (T)ys[i] - (A + B * f);
+                s0 += r; s1 += r * f; ss += r * r;
+            }
+            for (; i + 4 <= stop; i += 4) {
+                const float4 y4 = *reinterpret_cast<const float4*>(ys + i);
+                const float4 f4 = *reinterpret_cast<const float4*>(fs + i);
+                const T yv[4] = {(T)y4.x, (T)y4.y, (T)y4.z, (T)y4.w};
+                const T fv[4] = {(T)f4.x, (T)f4.y, (T)f4.z, (T)f4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const T r = yv[k] - (A + B * fv[k]);
+                    s0 += r; s1 += r * fv[k]; ss += r * r;
+                }
+            }
             for (; i < stop; ++i) {
                 const T f = (T)fs[i];
                 const T r = (T)ys[i] - (A + B * f);
@@ -149,7 +167,8 @@ int b2_hier_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
                    const B2ChainState* st, int n, double* logp, cudaStream_t stream) {
     const int N = e->md.N, NG = e->md.G;
     const int chain_tiles = (n + HT_CHAINS - 1) / HT_CHAINS;
-    int splits = (4 * e->sm_count + chain_tiles - 1) / chain_tiles;
+    // ~8 resident 128-thread blocks per SM and a grid that is a whole number of waves (148 SMs)
+    int splits = (8 * e->sm_count + chain_tiles / 2) / chain_tiles;
     if (splits > (N + 255) / 256) splits = (N + 255) / 256;
     if (splits < 1) splits = 1;
     int rows_per_split = (N + splits - 1) / splits;

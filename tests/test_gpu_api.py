@@ -210,3 +210,31 @@ def test_save_load_trace_roundtrip(tmp_path, schools_trace):
     assert back.nchains == 8 and len(back) == 50
     assert np.array_equal(back["mu"], trace[:50]["mu"])
     assert np.array_equal(back.get_sampler_stats("depth"), trace[:50].get_sampler_stats("depth"))
+
+
+def test_posterior_agrees_with_cpu_nuts_by_mcse_z_test():
+    """BASELINE.json north star: posterior means agree with the reference's CPU NUTS within an
+    MCSE-based |z| < 4 (CPU arm = the oracle port of the reference's step methods, 4 chains)."""
+    from oracle import densities as od
+    from oracle.hmc_cpu import CpuNUTS, run_chain
+    from oracle.potentials import DiagAdaptPotential
+    from oracle.rng import PhiloxRNG
+    from tests import models_util
+    X, y = models_util.glm_data(400, 4, seed=31)
+    oracle = od.LogisticGLM(X, y)
+    D = oracle.ndim
+    cpu = []
+    for c in range(4):
+        s = CpuNUTS(oracle, D, DiagAdaptPotential(D, np.zeros(D), np.ones(D), 10), PhiloxRNG(900 + c))
+        qs, _ = run_chain(s, np.zeros(D), 900, 400)
+        cpu.append(qs[400:])
+    cpu = np.stack(cpu)                                            # [4, 500, D]
+    with pm.LogisticGLM(X, y):
+        trace = pm.sample(500, tune=400, chains=64, random_seed=4, step=pm.NUTS(), compute_convergence_checks=False)
+    names = ["Intercept"] + ["x%d" % i for i in range(4)]
+    for j, name in enumerate(names):
+        gpu = np.stack(trace.get_values(name, combine=False))      # [64, 500]
+        se = np.hypot(float(pm.stats.mcse_mean(gpu)), float(pm.stats.mcse_mean(cpu[:, :, j])))
+        z = (gpu.mean() - cpu[:, :, j].mean()) / se
+        assert abs(z) < 4, (name, z)
+        assert abs(gpu.std() / cpu[:, :, j].std() - 1) < 0.12, name
