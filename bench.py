@@ -262,6 +262,7 @@ def run_b200(args):
     dev_ms = ev0.elapsed_time(ev1)
     clock_info = clocks.stop() if rank == 0 else None
     like_ms, like_n = eng.profile()
+    adv_ms = eng.profile_advance()
     launches = eng.kernel_launches() - launches0
     reports = eng.reports()
     failed = sum(1 for r in reports if r.phase != _capi.PHASE_DONE)
@@ -347,6 +348,7 @@ def run_b200(args):
                         "frac": ach / peaks["hbm_gbs"], "traffic": None}
         roofline.update({"kernel": "chain-batched likelihood (logp+dlogp, all chains)", "launches_timed": int(like_n),
                          "avg_launch_us": per_launch_s * 1e6, "kernel_share_of_step": like_ms / dev_ms,
+                         "advance_kernel_avg_us": adv_ms * 1e3 / like_n, "advance_share_of_step": adv_ms / dev_ms,
                          "peak_source": peaks["source"]})
 
     cpu = None

@@ -169,6 +169,7 @@ int64_t b2_kernel_launches(b2_engine* e);
  * since b2_set_profiling(e, 1). */
 int b2_set_profiling(b2_engine* e, int32_t on);
 int b2_get_profile(b2_engine* e, double* likelihood_ms, int64_t* likelihood_launches);
+int b2_get_profile_advance(b2_engine* e, double* advance_ms);   /* total ms of the advance kernel over the same launches */
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,7 @@ class ChainReport(C.Structure):
 
 EXPORTS = ["b2_abi_version", "b2_last_error", "b2_engine_create", "b2_engine_destroy", "b2_logp_dlogp",
            "b2_set_state", "b2_set_position", "b2_sample_run", "b2_get_chain_reports", "b2_get_mass_var", "b2_get_position",
-           "b2_kernel_launches", "b2_set_profiling", "b2_get_profile", "b2_step_begin", "b2_step_likelihood",
+           "b2_kernel_launches", "b2_set_profiling", "b2_get_profile", "b2_get_profile_advance", "b2_step_begin", "b2_step_likelihood",
            "b2_step_advance", "b2_step_active", "b2_step_end"]
 
 _lib = None
@@ -91,6 +91,7 @@ def load_library(path=None):
     lib.b2_step_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.b2_step_active.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
     lib.b2_step_end.argtypes = [C.c_void_p]
+    lib.b2_get_profile_advance.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.b2_set_profiling.argtypes = [C.c_void_p, C.c_int32]
     lib.b2_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name in EXPORTS:

@@ -60,8 +60,6 @@ struct B2ChainState {
     double log_size, log_accept, max_de, prop_energy, prop_logp;
     int n_prop, diverged, turned;
     unsigned long long slot_map;
-    double lv_log_size[B2_MAX_LEVELS], lv_log_accept[B2_MAX_LEVELS];
-    double lv_energy[B2_MAX_LEVELS], lv_logp[B2_MAX_LEVELS];
     // HMC
     int hmc_n_steps, hmc_step;
     // run counters
@@ -78,7 +76,10 @@ struct B2View {
     double* wv_mean;              // [2][C][Dp]  Welford means   (always fp64, quadpotential.py:321-327)
     double* wv_m2;                // [2][C][Dp]  Welford raw variances
     B2ChainState* st;             // [C]
+    double* lv;                   // [C][4][B2_MAX_LEVELS] per stack buffer: log_size, log_accept_sum, energy, logp
+                                  // (kept out of B2ChainState so the per-launch state copy stays ~230 B)
     double* logp_eval;            // [C]  written by the gradient kernel (lock-step mode)
+    long long* dbg;               // optional clock stamps of chain 0 (profiling builds of the lock-step kernels)
     // sampler options
     int kind;                     // NUTS | HMC
     int iter_base, iter_end, tune_until;
@@ -95,8 +96,15 @@ struct B2View {
     unsigned char *tr_diverging, *tr_tune, *tr_accepted;
 
     B2_HD T* V(int slot, int c) const { return vec + ((size_t)slot * C + c) * Dp; }
+    B2_HD double& LV(int c, int which, int buf) const { return lv[((size_t)c * 4 + which) * B2_MAX_LEVELS + buf]; }
     B2_HD T* S(int buf, int which, int c) const { return V(B2_V_STACK0 + buf * B2_S_NVEC + which, c); }
 };
+
+#if defined(__CUDA_ARCH__)
+#define B2_STAMP(w, c, s, k) do { if ((w).dbg && (c) == 0) (w).dbg[((s).n_grad & 4095) * 16 + (k)] = clock64(); } while (0)
+#else
+#define B2_STAMP(w, c, s, k) do { } while (0)
+#endif
 
 B2_HD bool b2_needs_grad(int phase) {
     return phase == B2_PHASE_INIT || phase == B2_PHASE_TREE || phase == B2_PHASE_HMC;
@@ -261,7 +269,6 @@ B2_HD void b2_init_chain(const G& g, const B2View<T>& w, int c, B2ChainState& s,
     s.depth = 0; s.max_depth = 0; s.dir = 1; s.leaf_n = 0;
     s.log_size = 0.0; s.log_accept = 0.0; s.max_de = 0.0; s.prop_energy = 0.0; s.prop_logp = 0.0;
     s.n_prop = 0; s.diverged = 0; s.turned = 0; s.slot_map = B2_MAP_IDENTITY;
-    for (int l = 0; l < B2_MAX_LEVELS; ++l) { s.lv_log_size[l] = 0; s.lv_log_accept[l] = 0; s.lv_energy[l] = 0; s.lv_logp[l] = 0; }
     s.hmc_n_steps = 0; s.hmc_step = 0;
     s.n_div_post = 0; s.n_maxdepth_post = 0; s.n_post = 0; s.n_grad = 0;
     T *pq = w.V(B2_V_PROPQ, c), *q1 = w.V(B2_V_QE1, c), *var = w.V(B2_V_VAR, c);
@@ -424,16 +431,16 @@ B2_HD int b2_top_merge(const G& g, const B2View<T>& w, int c, B2ChainState& s) {
     const int buf = b2_map_get(s.slot_map, d_old);
     s.depth += 1;
     s.n_prop += (1 << d_old);
-    const double sub_ls = s.lv_log_size[buf];
+    const double sub_ls = w.LV(c, 0, buf);
     const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_TOP, (uint32_t)d_old, 0u);
     if (log(u) < sub_ls - s.log_size) {                   // nuts.py:289-291
         b2_copy(g, w.D, w.V(B2_V_PROPQ, c), w.S(buf, B2_S_Q, c));
         b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.S(buf, B2_S_G, c));
-        s.prop_energy = s.lv_energy[buf];
-        s.prop_logp = s.lv_logp[buf];
+        s.prop_energy = w.LV(c, 2, buf);
+        s.prop_logp = w.LV(c, 3, buf);
     }
     s.log_size = b2_logaddexp(s.log_size, sub_ls);
-    s.log_accept = b2_logaddexp(s.log_accept, s.lv_log_accept[buf]);
+    s.log_accept = b2_logaddexp(s.log_accept, w.LV(c, 1, buf));
     const T* var = w.V(B2_V_VAR, c);
     T* psum = w.V(B2_V_PSUM, c);
     // dir=1: main tree | new sub-tree.   dir=0: new sub-tree (reversed in time) | main tree.
@@ -481,8 +488,8 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const T p = pe[i];
             sf[i] = p; sl[i] = p; ss[i] = p; sq[i] = qe[i]; sg[i] = ge[i];
         }
-        s.lv_log_size[buf] = leaf_ls; s.lv_log_accept[buf] = leaf_la;
-        s.lv_energy[buf] = energy; s.lv_logp[buf] = logp_new;
+        w.LV(c, 0, buf) = leaf_ls; w.LV(c, 1, buf) = leaf_la;
+        w.LV(c, 2, buf) = energy; w.LV(c, 3, buf) = logp_new;
     } else {
         for (int k = 0; k < j; ++k) {
             const int b1 = b2_map_get(s.slot_map, k);
@@ -493,24 +500,24 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const T* s2 = leaf2 ? pe : w.S(b2i, B2_S_PSUM, c);
             const T* q2 = leaf2 ? qe : w.S(b2i, B2_S_Q, c);
             const T* g2 = leaf2 ? ge : w.S(b2i, B2_S_G, c);
-            const double ls2 = leaf2 ? leaf_ls : s.lv_log_size[b2i];
-            const double la2 = leaf2 ? leaf_la : s.lv_log_accept[b2i];
-            const double en2 = leaf2 ? energy : s.lv_energy[b2i];
-            const double lp2 = leaf2 ? logp_new : s.lv_logp[b2i];
+            const double ls2 = leaf2 ? leaf_ls : w.LV(c, 0, b2i);
+            const double la2 = leaf2 ? leaf_la : w.LV(c, 1, b2i);
+            const double en2 = leaf2 ? energy : w.LV(c, 2, b2i);
+            const double lp2 = leaf2 ? logp_new : w.LV(c, 3, b2i);
             T *f1 = w.S(b1, B2_S_PFIRST, c), *l1 = w.S(b1, B2_S_PLAST, c), *s1 = w.S(b1, B2_S_PSUM, c);
             const bool turning = b2_uturn<T, G>(g, w.D, var, f1, l1, s1, f2, l2, s2, k > 0, s1, l1);
             if (turning) { s.turned = 1; break; }
-            const double ls1 = s.lv_log_size[b1];
+            const double ls1 = w.LV(c, 0, b1);
             const double ls = b2_logaddexp(ls1, ls2);
             const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_MERGE, (uint32_t)s.depth,
                                         ((uint32_t)(k + 1) << 16) | (uint32_t)n);
             if (log(u) < ls2 - ls) {                      // nuts.py:375-378
                 b2_copy(g, w.D, w.S(b1, B2_S_Q, c), q2);
                 b2_copy(g, w.D, w.S(b1, B2_S_G, c), g2);
-                s.lv_energy[b1] = en2; s.lv_logp[b1] = lp2;
+                w.LV(c, 2, b1) = en2; w.LV(c, 3, b1) = lp2;
             }
-            s.lv_log_size[b1] = ls;
-            s.lv_log_accept[b1] = b2_logaddexp(s.lv_log_accept[b1], la2);
+            w.LV(c, 0, b1) = ls;
+            w.LV(c, 1, b1) = b2_logaddexp(w.LV(c, 1, b1), la2);
         }
         if (s.turned) {
             s.depth += 1;
@@ -573,7 +580,9 @@ B2_HD bool b2_advance(const G& g, const B2View<T>& w, int c, B2ChainState& s, do
     } else if (s.phase == B2_PHASE_HMC) {
         act = b2_finish_hmc_step(g, w, c, s, logp_new, es);
     }
+    B2_STAMP(w, c, s, 3);
     if (act == B2_ACT_TOP_MERGE) act = b2_top_merge(g, w, c, s);
+    B2_STAMP(w, c, s, 4);
     if (act == B2_ACT_END_NUTS || act == B2_ACT_END_NUTS_MAXDEPTH) {
         es.accept_stat = 0.0;                             // nuts.py:391-397
         if (s.log_size > 0.0) {
@@ -590,7 +599,10 @@ B2_HD bool b2_advance(const G& g, const B2View<T>& w, int c, B2ChainState& s, do
         act = B2_ACT_END;
     }
     if (act == B2_ACT_END) act = b2_end_transition(g, w, c, s, es);
+    B2_STAMP(w, c, s, 5);
     if (act == B2_ACT_BEGIN_TRANSITION) act = b2_begin_transition(g, w, c, s);
+    B2_STAMP(w, c, s, 6);
     if (act == B2_ACT_BEGIN_DOUBLING) b2_begin_doubling(g, w, c, s);
+    B2_STAMP(w, c, s, 7);
     return s.phase == B2_PHASE_TREE || s.phase == B2_PHASE_HMC;
 }

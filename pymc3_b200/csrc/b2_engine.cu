@@ -151,7 +151,7 @@ static B2View<T> make_view(b2_engine* e) {
     B2View<T> w;
     memset(&w, 0, sizeof(w));
     w.C = e->C; w.D = e->D; w.Dp = e->Dp;
-    w.vec = (T*)e->vec; w.wv_mean = e->wv_mean; w.wv_m2 = e->wv_m2; w.st = e->st; w.logp_eval = e->logp_eval;
+    w.vec = (T*)e->vec; w.wv_mean = e->wv_mean; w.wv_m2 = e->wv_m2; w.st = e->st; w.lv = e->lv; w.logp_eval = e->logp_eval;
     return w;
 }
 
@@ -269,6 +269,8 @@ extern "C" int b2_engine_create(const b2_model_desc* desc, int32_t n_chains, int
     B2_CUDA_OK(cudaMalloc(&e->wv_m2, (size_t)2 * e->C * e->Dp * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&e->st, (size_t)e->C * sizeof(B2ChainState)));
     B2_CUDA_OK(cudaMemset(e->st, 0, (size_t)e->C * sizeof(B2ChainState)));
+    B2_CUDA_OK(cudaMalloc(&e->lv, (size_t)e->C * 4 * B2_MAX_LEVELS * sizeof(double)));
+    B2_CUDA_OK(cudaMemset(e->lv, 0, (size_t)e->C * 4 * B2_MAX_LEVELS * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&e->logp_eval, (size_t)e->C * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&e->d_active, sizeof(int)));
     B2_CUDA_OK(cudaMallocHost(&e->h_active, sizeof(int)));
@@ -279,11 +281,11 @@ extern "C" int b2_engine_create(const b2_model_desc* desc, int32_t n_chains, int
 extern "C" int b2_engine_destroy(b2_engine* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaFree(e->vec); cudaFree(e->wv_mean); cudaFree(e->wv_m2); cudaFree(e->st); cudaFree(e->logp_eval);
+    cudaFree(e->vec); cudaFree(e->wv_mean); cudaFree(e->wv_m2); cudaFree(e->st); cudaFree(e->lv); cudaFree(e->logp_eval);
     b2_glm_tc_release(e);
     cudaFree(e->glm_scratch); cudaFree(e->d_active); cudaFree(e->glm_ws); cudaFree(e->hier_ws);
     cudaFreeHost(e->h_active);
-    if (e->ev[0]) for (int i = 0; i < 64; ++i) cudaEventDestroy(e->ev[i]);
+    if (e->ev[0]) for (int i = 0; i < 96; ++i) cudaEventDestroy(e->ev[i]);
     delete e;
     return 0;
 }
@@ -420,11 +422,11 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         }
         for (;;) {
             for (int b = 0; b < batch; ++b) {
-                if (e->profile) cudaEventRecord(e->ev[2 * b], s);
+                if (e->profile) cudaEventRecord(e->ev[3 * b], s);
                 int rc = fused_tc ? b2_glm_tc_main(e, s)
                                   : launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
                 if (rc) return rc;
-                if (e->profile) cudaEventRecord(e->ev[2 * b + 1], s);
+                if (e->profile) cudaEventRecord(e->ev[3 * b + 1], s);
                 if (fused_tc) {
                     rc = b2_glm_tc_post(e, &w, s);
                     if (rc) return rc;
@@ -433,6 +435,7 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
                     else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 0);
                     e->launches += 1;
                 }
+                if (e->profile) cudaEventRecord(e->ev[3 * b + 2], s);
             }
             B2_CUDA_OK(cudaMemsetAsync(e->d_active, 0, sizeof(int), s));
             k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, e->d_active);
@@ -442,7 +445,8 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
             if (e->profile) {
                 for (int b = 0; b < batch; ++b) {
                     float ms = 0.f;
-                    if (cudaEventElapsedTime(&ms, e->ev[2 * b], e->ev[2 * b + 1]) == cudaSuccess) { e->like_ms += ms; e->like_n += 1; }
+                    if (cudaEventElapsedTime(&ms, e->ev[3 * b], e->ev[3 * b + 1]) == cudaSuccess) { e->like_ms += ms; e->like_n += 1; }
+                    if (cudaEventElapsedTime(&ms, e->ev[3 * b + 1], e->ev[3 * b + 2]) == cudaSuccess) e->adv_ms += ms;
                 }
             }
             if (*e->h_active == 0) break;
@@ -644,14 +648,20 @@ extern "C" int b2_set_profiling(b2_engine* e, int32_t on) {
     if (!e) { b2_set_error("b2_set_profiling: null engine"); return -1; }
     B2_CUDA_OK(cudaSetDevice(e->device));
     if (on && !e->ev[0])
-        for (int i = 0; i < 64; ++i) B2_CUDA_OK(cudaEventCreate(&e->ev[i]));
+        for (int i = 0; i < 96; ++i) B2_CUDA_OK(cudaEventCreate(&e->ev[i]));
     e->profile = on ? 1 : 0;
-    e->like_ms = 0.0; e->like_n = 0;
+    e->like_ms = 0.0; e->like_n = 0; e->adv_ms = 0.0;
     return 0;
 }
 
 extern "C" int b2_get_profile(b2_engine* e, double* likelihood_ms, int64_t* likelihood_launches) {
     if (!e || !likelihood_ms || !likelihood_launches) { b2_set_error("b2_get_profile: null argument"); return -1; }
     *likelihood_ms = e->like_ms; *likelihood_launches = e->like_n;
+    return 0;
+}
+
+extern "C" int b2_get_profile_advance(b2_engine* e, double* advance_ms) {
+    if (!e || !advance_ms) { b2_set_error("b2_get_profile_advance: null argument"); return -1; }
+    *advance_ms = e->adv_ms;
     return 0;
 }

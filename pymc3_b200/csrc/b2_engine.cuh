@@ -14,6 +14,7 @@ struct b2_engine {
     double* wv_mean;           // [2][C][Dp]
     double* wv_m2;
     B2ChainState* st;          // [C]
+    double* lv;                // [C][4][B2_MAX_LEVELS] stack-buffer scalars
     double* logp_eval;         // [C]
     void* glm_scratch;         // lazily allocated [C][N] for the group evaluator
     int* d_active;             // device counter
@@ -35,7 +36,8 @@ struct b2_engine {
     int profile;
     double like_ms;
     int64_t like_n;
-    cudaEvent_t ev[64];
+    double adv_ms;             // advance / post kernel, same launches
+    cudaEvent_t ev[96];        // per batch step b: ev[3b] | likelihood | ev[3b+1] | advance | ev[3b+2]
 };
 
 void b2_set_error(const std::string& msg);

@@ -441,10 +441,14 @@ __device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int c
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* gp = reinterpret_cast<const float4*>(ws.gpart + (size_t)chain * TC_KP) + lane;
     const size_t stride4 = (size_t)ws.c_pad * TC_KP / 4;
-#pragma unroll 6
-    for (int sp = 0; sp < ws.splits; ++sp) {
-        const float4 v = gp[sp * stride4];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    // all slab partials of this lane in flight at once (one L2 round trip), then a fixed-order sum
+    for (int sp0 = 0; sp0 < ws.splits; sp0 += 24) {
+        float4 v[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j)
+            v[j] = (sp0 + j < ws.splits) ? __ldcg(gp + (size_t)(sp0 + j) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
     }
     const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
     double prior = 0.0;
@@ -495,14 +499,20 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= w.C) return;
     B2WarpGroup g;
+    w.dbg = ws.dbg ? ws.dbg + 48 * TC_DBG_TILES : nullptr;          // post-kernel stamps live behind the main kernel's
+    const long long t_start = clock64();
     B2ChainState s = w.st[c];
     if (!b2_needs_grad(s.phase)) return;
+    if (w.dbg && c == 0) w.dbg[(s.n_grad & 4095) * 16 + 0] = t_start;
+    B2_STAMP(w, c, s, 1);
     const float* q = w.V(B2_V_QE0 + s.sel, c);
     float* gr = w.V(B2_V_GE0 + s.sel, c);
     const double lp = tc_finalize_chain(ws, c, g.lane(), K1, prior_tau, q, gr);
     __syncwarp();
+    B2_STAMP(w, c, s, 2);
     b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
     if (g.lane() == 0) w.st[c] = s;
+    if (w.dbg && c == 0) { __threadfence(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 8] = clock64(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 9] = s.leaf_n * 100 + s.depth; }
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -535,8 +545,8 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     B2_CUDA_OK(cudaMalloc(&w.err, sizeof(int)));
     w.dbg = nullptr;
     if (getenv("B2_TC_TIMELINE")) {
-        B2_CUDA_OK(cudaMalloc(&w.dbg, 48 * TC_DBG_TILES * sizeof(long long)));
-        B2_CUDA_OK(cudaMemsetAsync(w.dbg, 0, 48 * TC_DBG_TILES * sizeof(long long), stream));
+        B2_CUDA_OK(cudaMalloc(&w.dbg, (48 * TC_DBG_TILES + 4096 * 16) * sizeof(long long)));
+        B2_CUDA_OK(cudaMemsetAsync(w.dbg, 0, (48 * TC_DBG_TILES + 4096 * 16) * sizeof(long long), stream));
     }
     B2_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), stream));
     k_glm_tc_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt, w.n_tiles);
@@ -585,6 +595,16 @@ extern "C" int b2_debug_tc_timeline(b2_engine* e, long long* host_out) {
     if (!w.dbg) return -2;
     B2_CUDA_OK(cudaDeviceSynchronize());
     B2_CUDA_OK(cudaMemcpy(host_out, w.dbg, 48 * TC_DBG_TILES * sizeof(long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// clock64 stamps of chain 0 inside k_glm_tc_post, one row of 16 per leapfrog (ring of 4096)
+extern "C" int b2_debug_post_timeline(b2_engine* e, long long* host_out) {
+    if (!e || !e->glm_tc) return -1;
+    TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
+    if (!w.dbg) return -2;
+    B2_CUDA_OK(cudaDeviceSynchronize());
+    B2_CUDA_OK(cudaMemcpy(host_out, w.dbg + 48 * TC_DBG_TILES, 4096 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 

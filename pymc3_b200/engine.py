@@ -167,5 +167,11 @@ class Engine:
         _capi.check(self.lib.b2_get_profile(self.handle, C.byref(ms), C.byref(n)), self.lib)
         return ms.value, n.value
 
+    def profile_advance(self):
+        """total ms of the advance (state machine) kernel over the launches counted by profile()."""
+        ms = C.c_double()
+        _capi.check(self.lib.b2_get_profile_advance(self.handle, C.byref(ms)), self.lib)
+        return ms.value
+
     def kernel_launches(self):
         return int(self.lib.b2_kernel_launches(self.handle))

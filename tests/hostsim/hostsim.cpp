@@ -17,11 +17,12 @@ static int run_t(const B2ModelData& md, int C, const double* q0, const uint64_t*
     std::vector<T> vec((size_t)B2_NUM_VEC_SLOTS * C * Dp, (T)0);
     std::vector<double> wm((size_t)2 * C * Dp, 0.0), w2((size_t)2 * C * Dp, 0.0), lp(C, 0.0);
     std::vector<B2ChainState> st(C);
+    std::vector<double> lv((size_t)C * 4 * B2_MAX_LEVELS, 0.0);
     std::vector<T> scratch((size_t)(md.family == B2_FAMILY_GLM_LOGIT ? md.N : 1));
     B2View<T> w;
     memset(&w, 0, sizeof(w));
     w.C = C; w.D = D; w.Dp = Dp; w.vec = vec.data(); w.wv_mean = wm.data(); w.wv_m2 = w2.data();
-    w.st = st.data(); w.logp_eval = lp.data();
+    w.st = st.data(); w.lv = lv.data(); w.logp_eval = lp.data();
     w.kind = o->kind; w.iter_base = 0; w.iter_end = o->n_iters; w.tune_until = o->tune_until;
     w.max_treedepth = o->max_treedepth; w.early_max_treedepth = o->early_max_treedepth;
     w.emax = o->Emax; w.target = o->target_accept; w.gamma = o->gamma; w.k = o->k; w.t0 = o->t0;
