@@ -95,7 +95,14 @@ struct B2View {
     int *tr_depth, *tr_tree_size, *tr_n_steps;
     unsigned char *tr_diverging, *tr_tune, *tr_accepted;
 
-    B2_HD T* V(int slot, int c) const { return vec + ((size_t)slot * C + c) * Dp; }
+    // Optional on-chip copy of THIS chain's hot slots (edges, p_old, p_sum, proposal, var):
+    // [B2_V_STACK0][Dp], staged in shared memory by the kernel for the duration of one launch.
+    T* hot;
+    B2_HD T* V(int slot, int c) const {
+        if (hot && slot < B2_V_STACK0) return hot + (size_t)slot * Dp;
+        return vec + ((size_t)slot * C + c) * Dp;
+    }
+    B2_HD T* Vglobal(int slot, int c) const { return vec + ((size_t)slot * C + c) * Dp; }
     B2_HD double& LV(int c, int which, int buf) const { return lv[((size_t)c * 4 + which) * B2_MAX_LEVELS + buf]; }
     B2_HD T* S(int buf, int which, int c) const { return V(B2_V_STACK0 + buf * B2_S_NVEC + which, c); }
 };

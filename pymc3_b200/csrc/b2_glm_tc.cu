@@ -438,6 +438,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
 // lane l owns features 4l..4l+3 (one float4 per slab partial).
 __device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int chain, int lane, int K1, double prior_tau,
                                                     const float* q, float* g) {
+    // logp slab partials first, so their round trip overlaps the gradient partials'
+    const int n_lp = ws.splits * TC_EPI_GROUPS;
+    double lpv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        lpv[j] = (lane + 32 * j < n_lp) ? __ldcg(ws.lpart + (size_t)(lane + 32 * j) * ws.c_pad + chain) : 0.0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* gp = reinterpret_cast<const float4*>(ws.gpart + (size_t)chain * TC_KP) + lane;
     const size_t stride4 = (size_t)ws.c_pad * TC_KP / 4;
@@ -452,6 +458,7 @@ __device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int c
     }
     const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
     double prior = 0.0;
+    const double prior_const = 0.5 * (log(prior_tau) - B2_LOG_2PI);    // once per warp, not per coefficient
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int k = 4 * lane + j;
@@ -460,13 +467,13 @@ __device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int c
             if (k > 0) {
                 const double b = (double)q[k];
                 sgrad -= prior_tau * b;
-                prior += 0.5 * (-prior_tau * b * b + log(prior_tau) - B2_LOG_2PI);
+                prior += -0.5 * prior_tau * b * b + prior_const;
             }
             g[k] = (float)sgrad;
         }
     }
-    double lp = 0.0;
-    for (int sp = lane; sp < ws.splits * TC_EPI_GROUPS; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
+    double lp = (lpv[0] + lpv[1]) + (lpv[2] + lpv[3]);
+    for (int sp = lane + 128; sp < n_lp; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
     for (int o = 16; o > 0; o >>= 1) {
         prior += __shfl_xor_sync(0xffffffffu, prior, o);
         lp += __shfl_xor_sync(0xffffffffu, lp, o);
@@ -501,8 +508,23 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
     B2WarpGroup g;
     w.dbg = ws.dbg ? ws.dbg + 48 * TC_DBG_TILES : nullptr;          // post-kernel stamps live behind the main kernel's
     const long long t_start = clock64();
+    __shared__ __align__(16) float hot_s[4][B2_V_STACK0 * 128];
+    // stage this chain's 11 hot vector slots in shared memory: issued together with the state load
+    float* hot = hot_s[threadIdx.x >> 5];
+    {
+        const int lane = threadIdx.x & 31;
+        float4 tmp[B2_V_STACK0];
+#pragma unroll
+        for (int slot = 0; slot < B2_V_STACK0; ++slot)
+            tmp[slot] = (4 * lane < w.Dp) ? *reinterpret_cast<const float4*>(w.Vglobal(slot, c) + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int slot = 0; slot < B2_V_STACK0; ++slot)
+            if (4 * lane < w.Dp) *reinterpret_cast<float4*>(hot + slot * w.Dp + 4 * lane) = tmp[slot];
+    }
     B2ChainState s = w.st[c];
     if (!b2_needs_grad(s.phase)) return;
+    __syncwarp();
+    w.hot = hot;
     if (w.dbg && c == 0) w.dbg[(s.n_grad & 4095) * 16 + 0] = t_start;
     B2_STAMP(w, c, s, 1);
     const float* q = w.V(B2_V_QE0 + s.sel, c);
@@ -512,6 +534,15 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
     B2_STAMP(w, c, s, 2);
     b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
     if (g.lane() == 0) w.st[c] = s;
+    __syncwarp();
+    {   // write the hot slots back (the likelihood kernel and the next launch read them from HBM/L2)
+        const int lane = threadIdx.x & 31;
+        if (4 * lane < w.Dp) {
+#pragma unroll
+            for (int slot = 0; slot < B2_V_STACK0; ++slot)
+                *reinterpret_cast<float4*>(w.Vglobal(slot, c) + 4 * lane) = *reinterpret_cast<const float4*>(hot + slot * w.Dp + 4 * lane);
+        }
+    }
     if (w.dbg && c == 0) { __threadfence(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 8] = clock64(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 9] = s.leaf_n * 100 + s.depth; }
 }
 
