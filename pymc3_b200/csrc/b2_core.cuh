@@ -171,11 +171,33 @@ struct B2BlockGroup {                      // block per chain (large D)
 #endif
 
 // ----------------------------------------------------------------------------- small math
+// Scalar transcendentals of the tree bookkeeping.  The fp64 check build evaluates them in double (to
+// match the oracle draw for draw); the fp32 production build evaluates the *transcendental part* in
+// float -- they only feed log-weights / acceptance probabilities, where 1e-7 relative is far below the
+// Monte-Carlo noise, and a single warp executing double log/exp/pow chains was a visible share of the
+// lock-step advance kernel (profiles/post_timeline.py).  Energies and log-densities stay fp64.
+template <typename T> struct B2M;
+template <> struct B2M<double> {
+    B2_HD static double log_(double x) { return log(x); }
+    B2_HD static double exp_(double x) { return exp(x); }
+    B2_HD static double log1p_(double x) { return log1p(x); }
+    B2_HD static double expm1_(double x) { return expm1(x); }
+    B2_HD static double pow_(double x, double y) { return pow(x, y); }
+};
+template <> struct B2M<float> {
+    B2_HD static double log_(double x) { return (double)logf((float)x); }
+    B2_HD static double exp_(double x) { return (double)expf((float)x); }
+    B2_HD static double log1p_(double x) { return (double)log1pf((float)x); }
+    B2_HD static double expm1_(double x) { return (double)expm1f((float)x); }
+    B2_HD static double pow_(double x, double y) { return (double)powf((float)x, (float)y); }
+};
+
+template <typename T>
 B2_HD double b2_logaddexp(double a, double b) {          // numpy.logaddexp semantics
     if (a == b) return a + 0.693147180559945309417232121458;
     double d = a - b;
-    if (d > 0) return a + log1p(exp(-d));
-    if (d <= 0) return b + log1p(exp(d));
+    if (d > 0) return a + B2M<T>::log1p_(B2M<T>::exp_(-d));
+    if (d <= 0) return b + B2M<T>::log1p_(B2M<T>::exp_(d));
     return a + b;                                        // NaN
 }
 B2_HD bool b2_finite(double x) { return (x - x) == 0.0; }
@@ -299,7 +321,7 @@ struct B2EndStats { double accept_stat, energy, energy_error, model_logp; bool a
 template <typename T, typename G>
 B2_HD void b2_begin_doubling(const G& g, const B2View<T>& w, int c, B2ChainState& s) {
     const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_DIRECTION, (uint32_t)s.depth, 0u);
-    s.dir = (log(u) < -0.693147180559945309417232121458) ? 1 : 0;        // nuts.py:177
+    s.dir = (u < 0.5) ? 1 : 0;                              // log(u) < log(0.5)        // nuts.py:177
     b2_copy(g, w.D, w.V(B2_V_POLD, c), w.V(B2_V_PE0 + s.dir, c));
     s.leaf_n = 0;
     s.slot_map = B2_MAP_IDENTITY;
@@ -336,7 +358,7 @@ B2_HD int b2_begin_transition(const G& g, const B2View<T>& w, int c, B2ChainStat
         return B2_ACT_NONE;
     }
     const bool adapt = tune && w.adapt_step;
-    s.step_used = adapt ? exp(s.log_step) : exp(s.log_bar);   // step_sizes.py:34-38
+    s.step_used = B2M<T>::exp_(adapt ? s.log_step : s.log_bar);   // step_sizes.py:34-38
     s.eps = s.step_used;
     s.diverged = 0; s.turned = 0;
     if (nuts) {
@@ -367,7 +389,7 @@ B2_HD int b2_end_transition(const G& g, const B2View<T>& w, int c, B2ChainState&
         const double ww = 1.0 / (cnt + w.t0);
         s.hbar = (1.0 - ww) * s.hbar + ww * (w.target - es.accept_stat);
         s.log_step = s.mu - s.hbar * sqrt(cnt) / w.gamma;
-        const double mk = pow(cnt, -w.k);
+        const double mk = B2M<T>::pow_(cnt, -w.k);
         s.log_bar = mk * s.log_step + (1.0 - mk) * s.log_bar;
         s.da_count += 1;
     }
@@ -411,8 +433,8 @@ B2_HD int b2_end_transition(const G& g, const B2View<T>& w, int c, B2ChainState&
         if (w.tr_energy) w.tr_energy[o] = es.energy;
         if (w.tr_energy_error) w.tr_energy_error[o] = es.energy_error;
         if (w.tr_model_logp) w.tr_model_logp[o] = es.model_logp;
-        if (w.tr_step_size) w.tr_step_size[o] = exp(s.log_step);           // step_sizes.py:54-58
-        if (w.tr_step_size_bar) w.tr_step_size_bar[o] = exp(s.log_bar);
+        if (w.tr_step_size) w.tr_step_size[o] = B2M<T>::exp_(s.log_step);           // step_sizes.py:54-58
+        if (w.tr_step_size_bar) w.tr_step_size_bar[o] = B2M<T>::exp_(s.log_bar);
         if (w.tr_diverging) w.tr_diverging[o] = (unsigned char)(s.diverged != 0);
         if (w.tr_tune) w.tr_tune[o] = (unsigned char)tune;
         if (w.kind == B2_KIND_NUTS) {
@@ -440,14 +462,14 @@ B2_HD int b2_top_merge(const G& g, const B2View<T>& w, int c, B2ChainState& s) {
     s.n_prop += (1 << d_old);
     const double sub_ls = w.LV(c, 0, buf);
     const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_TOP, (uint32_t)d_old, 0u);
-    if (log(u) < sub_ls - s.log_size) {                   // nuts.py:289-291
+    if (B2M<T>::log_(u) < sub_ls - s.log_size) {                   // nuts.py:289-291
         b2_copy(g, w.D, w.V(B2_V_PROPQ, c), w.S(buf, B2_S_Q, c));
         b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.S(buf, B2_S_G, c));
         s.prop_energy = w.LV(c, 2, buf);
         s.prop_logp = w.LV(c, 3, buf);
     }
-    s.log_size = b2_logaddexp(s.log_size, sub_ls);
-    s.log_accept = b2_logaddexp(s.log_accept, w.LV(c, 1, buf));
+    s.log_size = b2_logaddexp<T>(s.log_size, sub_ls);
+    s.log_accept = b2_logaddexp<T>(s.log_accept, w.LV(c, 1, buf));
     const T* var = w.V(B2_V_VAR, c);
     T* psum = w.V(B2_V_PSUM, c);
     // dir=1: main tree | new sub-tree.   dir=0: new sub-tree (reversed in time) | main tree.
@@ -515,16 +537,16 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const bool turning = b2_uturn<T, G>(g, w.D, var, f1, l1, s1, f2, l2, s2, k > 0, s1, l1);
             if (turning) { s.turned = 1; break; }
             const double ls1 = w.LV(c, 0, b1);
-            const double ls = b2_logaddexp(ls1, ls2);
+            const double ls = b2_logaddexp<T>(ls1, ls2);
             const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_MERGE, (uint32_t)s.depth,
                                         ((uint32_t)(k + 1) << 16) | (uint32_t)n);
-            if (log(u) < ls2 - ls) {                      // nuts.py:375-378
+            if (B2M<T>::log_(u) < ls2 - ls) {                      // nuts.py:375-378
                 b2_copy(g, w.D, w.S(b1, B2_S_Q, c), q2);
                 b2_copy(g, w.D, w.S(b1, B2_S_G, c), g2);
                 w.LV(c, 2, b1) = en2; w.LV(c, 3, b1) = lp2;
             }
             w.LV(c, 0, b1) = ls;
-            w.LV(c, 1, b1) = b2_logaddexp(w.LV(c, 1, b1), la2);
+            w.LV(c, 1, b1) = b2_logaddexp<T>(w.LV(c, 1, b1), la2);
         }
         if (s.turned) {
             s.depth += 1;
@@ -550,7 +572,7 @@ B2_HD int b2_finish_hmc_step(const G& g, const B2View<T>& w, int c, B2ChainState
     double de = s.e0 - energy;
     if (de != de) de = -INFINITY;
     if (fabs(de) > w.emax) div = true;                    // :129
-    const double ex = exp(de);
+    const double ex = B2M<T>::exp_(de);
     const double accept = ex < 1.0 ? ex : 1.0;
     bool accepted = false;
     if (!div) {
@@ -593,12 +615,12 @@ B2_HD bool b2_advance(const G& g, const B2View<T>& w, int c, B2ChainState& s, do
     if (act == B2_ACT_END_NUTS || act == B2_ACT_END_NUTS_MAXDEPTH) {
         es.accept_stat = 0.0;                             // nuts.py:391-397
         if (s.log_size > 0.0) {
-            es.accept_stat = exp(s.log_accept) / expm1(s.log_size);
+            es.accept_stat = B2M<T>::exp_(s.log_accept) / B2M<T>::expm1_(s.log_size);
             // Deliberate deviation: for energy drops > ~709 (still below Emax = 1000) the reference's
             // exp()/expm1() is inf/inf = NaN, which poisons dual averaging for the rest of the chain.
             // Same quantity in log space, used only where the reference's expression is not finite.
             if (!b2_finite(es.accept_stat))
-                es.accept_stat = exp(s.log_accept - (s.log_size + log1p(-exp(-s.log_size))));
+                es.accept_stat = B2M<T>::exp_(s.log_accept - (s.log_size + B2M<T>::log1p_(-B2M<T>::exp_(-s.log_size))));
         }
         if (act == B2_ACT_END_NUTS_MAXDEPTH && !(s.iter < w.tune_until)) s.n_maxdepth_post += 1;   // nuts.py:182-184
         s.cur_logp = s.prop_logp;
