@@ -103,7 +103,11 @@ struct B2View {
         return vec + ((size_t)slot * C + c) * Dp;
     }
     B2_HD T* Vglobal(int slot, int c) const { return vec + ((size_t)slot * C + c) * Dp; }
-    B2_HD double& LV(int c, int which, int buf) const { return lv[((size_t)c * 4 + which) * B2_MAX_LEVELS + buf]; }
+    double* lv_hot;               // optional shared-memory copy of this chain's [4][B2_MAX_LEVELS] scalars
+    B2_HD double& LV(int c, int which, int buf) const {
+        if (lv_hot) return lv_hot[which * B2_MAX_LEVELS + buf];
+        return lv[((size_t)c * 4 + which) * B2_MAX_LEVELS + buf];
+    }
     B2_HD T* S(int buf, int which, int c) const { return V(B2_V_STACK0 + buf * B2_S_NVEC + which, c); }
 };
 

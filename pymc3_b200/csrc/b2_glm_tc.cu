@@ -521,10 +521,21 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
         for (int slot = 0; slot < B2_V_STACK0; ++slot)
             if (4 * lane < w.Dp) *reinterpret_cast<float4*>(hot + slot * w.Dp + 4 * lane) = tmp[slot];
     }
+    __shared__ double lv_s[4][4 * B2_MAX_LEVELS];
+    double* lvh = lv_s[threadIdx.x >> 5];
+    {
+        const int lane = threadIdx.x & 31;
+        const double* src = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
+        const double a0 = src[lane];
+        const double a1 = (lane + 32 < 4 * B2_MAX_LEVELS) ? src[lane + 32] : 0.0;
+        lvh[lane] = a0;
+        if (lane + 32 < 4 * B2_MAX_LEVELS) lvh[lane + 32] = a1;
+    }
     B2ChainState s = w.st[c];
     if (!b2_needs_grad(s.phase)) return;
     __syncwarp();
     w.hot = hot;
+    w.lv_hot = lvh;
     if (w.dbg && c == 0) w.dbg[(s.n_grad & 4095) * 16 + 0] = t_start;
     B2_STAMP(w, c, s, 1);
     const float* q = w.V(B2_V_QE0 + s.sel, c);
@@ -537,6 +548,9 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
     __syncwarp();
     {   // write the hot slots back (the likelihood kernel and the next launch read them from HBM/L2)
         const int lane = threadIdx.x & 31;
+        double* dst = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
+        dst[lane] = lvh[lane];
+        if (lane + 32 < 4 * B2_MAX_LEVELS) dst[lane + 32] = lvh[lane + 32];
         if (4 * lane < w.Dp) {
 #pragma unroll
             for (int slot = 0; slot < B2_V_STACK0; ++slot)
