@@ -90,9 +90,14 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
         raise NotImplementedError("pymc3_b200.sample runs NUTS / HamiltonianMC step methods only")
     if start is None:
         start = [model.test_point] * chains
-    if trace is not None or chain_idx != 0:
-        if not isinstance(trace, MultiTrace) and trace is not None:
+    if trace is not None:
+        # resume: new draws are appended to an in-memory MultiTrace and every chain starts from its last
+        # point (sampling.py:893-894, ndarray.py:221-231); like the reference, sampler state is not restored
+        if not isinstance(trace, MultiTrace):
             raise NotImplementedError("only in-memory MultiTrace continuation is supported")
+        if trace.nchains != chains:
+            raise ValueError("trace has %d chains, but chains=%d" % (trace.nchains, chains))
+        start = [{k: v for k, v in trace.point(-1, chain=c).items() if k in model.free_RVs} for c in trace.chains]
 
     t_start = time.time()
     mtrace = _sample_batched(step, model, draws, tune, chains, start, random_seed, devices, chain_idx)
@@ -100,6 +105,8 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
 
     discard = tune if discard_tuned_samples else 0
     mtrace = mtrace[discard:]                             # :556-557
+    if trace is not None:
+        mtrace = _append_traces(trace, mtrace)
     mtrace.report._n_tune = int(tune)
     mtrace.report._n_draws = int(draws - tune)
     mtrace.report._t_sampling = t_sampling
@@ -110,6 +117,21 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
             mtrace.report._run_convergence_checks(mtrace, model)
     mtrace.report._log_summary()
     return mtrace
+
+
+def _append_traces(old, new):
+    """Per chain: concatenate the draws and sampler stats of `new` behind those of `old`."""
+    straces = []
+    for c_old, c_new in zip(old.chains, new.chains):
+        a, b = old._straces[c_old], new._straces[c_new]
+        samples = {k: np.concatenate([a.samples[k], b.samples[k]]) for k in b.samples}
+        stats = None
+        if a._stats is not None and b._stats is not None:
+            stats = {k: np.concatenate([a._stats[0][k], b._stats[0][k]]) for k in b._stats[0]}
+        st = NDArray.from_arrays(new._straces[c_new].model, c_old, samples, stats)
+        st._add_warnings(getattr(a, "_warnings", []) + getattr(b, "_warnings", []))
+        straces.append(st)
+    return MultiTrace(straces)
 
 
 def _check_start_shape(model, start):

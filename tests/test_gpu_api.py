@@ -238,3 +238,14 @@ def test_posterior_agrees_with_cpu_nuts_by_mcse_z_test():
         z = (gpu.mean() - cpu[:, :, j].mean()) / se
         assert abs(z) < 4, (name, z)
         assert abs(gpu.std() / cpu[:, :, j].std() - 1) < 0.12, name
+
+
+def test_resume_from_existing_trace():
+    """sampling.py:893-894: passing trace= continues every chain from its last point and appends."""
+    with pm.StdNormal(3):
+        first = pm.sample(40, tune=40, chains=3, random_seed=1, compute_convergence_checks=False)
+        more = pm.sample(25, tune=0, chains=3, random_seed=2, trace=first, step=pm.NUTS(adapt_step_size=False),
+                         compute_convergence_checks=False)
+    assert len(more) == 65 and more.nchains == 3
+    assert np.array_equal(more.get_values("x", chains=1)[:40], first.get_values("x", chains=1))
+    assert more.get_sampler_stats("depth", chains=0).shape == (65,)
