@@ -52,10 +52,18 @@ struct TcWorkspace {
     int* err;                // device watchdog flag
     // per launch: where every chain's pending position lives
     const float* qA; const float* qB; int ld; const B2ChainState* st; int n_chains; int K1;
+    // active-chain compaction: chains that still need a gradient are packed into dense 128-row tiles, so a
+    // step costs ceil(n_active/128) chain tiles instead of all of them (early tuning and the tail of a run
+    // chunk leave most chains idle); the grid is fixed and re-divides its CTAs over the live tiles.
+    int* counters;           // [2] number of active chains for step parity p / p^1
+    int* chain_of_slot;      // [c_pad]
+    int* slot_of_chain;      // [c_pad]
+    int parity;              // which counter this launch reads
+    int grid_ctas;           // CTAs of the main grid
     long long* dbg;          // optional timeline of CTA (0,0): [event][tile] clock64 stamps (B2_TC_TIMELINE=1)
 };
 #define TC_DBG_TILES 256
-#define TC_STAMP(ev, t) do { if (ws.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (t) < TC_DBG_TILES) ws.dbg[(ev) * TC_DBG_TILES + (t)] = clock64(); } while (0)
+#define TC_STAMP(ev, t) do { if (ws.dbg && blockIdx.x == 0 && (t) < TC_DBG_TILES) ws.dbg[(ev) * TC_DBG_TILES + (t)] = clock64(); } while (0)
 
 // byte offset of element (row, col) inside a [rows][64]-bf16 atom with the 128B swizzle
 // (Swizzle<3,4,3>: 16-byte chunk index ^= row % 8) -- the image TMA SWIZZLE_128B would produce.
@@ -180,6 +188,31 @@ __device__ __forceinline__ float tc_rcp(float x) { float y; asm("rcp.approx.ftz.
 #define TC_IDESC_G1 (TC_IDESC_BASE | ((TC_OBS >> 3) << 17) | ((TC_CHAINS >> 4) << 24))               // N=64,  K-major B
 #define TC_IDESC_G2 (TC_IDESC_BASE | (1u << 16) | ((TC_KP >> 3) << 17) | ((TC_CHAINS >> 4) << 24))   // N=128, MN-major B
 
+struct TcGeom { int n_act, nt, sp, tps, stride; };     // active chains, live tiles, row slabs, tiles per slab, slots
+__device__ __forceinline__ TcGeom tc_geom(const TcWorkspace& ws) {
+    TcGeom g;
+    g.n_act = ws.counters[ws.parity];
+    g.nt = (g.n_act + TC_CHAINS - 1) / TC_CHAINS;
+    g.sp = g.nt > 0 ? ws.grid_ctas / g.nt : 1;
+    if (g.sp > ws.n_tiles) g.sp = ws.n_tiles;
+    g.tps = (ws.n_tiles + g.sp - 1) / g.sp;
+    g.sp = (ws.n_tiles + g.tps - 1) / g.tps;            // slabs that actually own rows
+    g.stride = g.nt * TC_CHAINS;
+    return g;
+}
+
+// (re)builds the slot <-> chain maps from the chain states (first step of a run / parity hook)
+__global__ void k_glm_tc_compact(TcWorkspace ws, const B2ChainState* st, int n_chains) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    const bool live = st ? b2_needs_grad(st[c].phase) : true;
+    if (!live) return;
+    const int slot = st ? atomicAdd(ws.counters + ws.parity, 1) : c;
+    ws.chain_of_slot[slot] = c;
+    ws.slot_of_chain[c] = slot;
+    if (!st && c == 0) ws.counters[ws.parity] = n_chains;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -197,10 +230,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ctile = blockIdx.x, split = blockIdx.y;
-    const int t_begin = split * ws.tiles_per_split;
-    const int t_end = min(ws.n_tiles, t_begin + ws.tiles_per_split);
-    const int T = t_end - t_begin;                 // >= 1 by construction of the grid
+    const TcGeom gm = tc_geom(ws);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters[ws.parity ^ 1] = 0;   // k_glm_tc_post of this step refills it
+    const int ctile = blockIdx.x / gm.sp, split = blockIdx.x % gm.sp;
+    if (gm.nt == 0 || ctile >= gm.nt) return;      // whole CTA: no live chain tile for it
+    const int t_begin = split * gm.tps;
+    const int t_end = min(ws.n_tiles, t_begin + gm.tps);
+    const int T = t_end - t_begin;                 // >= 1: gm.sp counts only slabs that own rows
 
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, TC_EPI_WARPS);
@@ -306,10 +342,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
         // tile): the two pairs run one tile apart, so MUFU-heavy math of one pair overlaps the TMEM
         // loads / stores / barrier waits of the other instead of all 16 warps marching in lock-step.
         {   // Q (A operand of GEMM1): this thread's chain row, features 32cg..32cg+31, bf16 hi/lo split
-            const int chain = ctile * TC_CHAINS + row;
-            bool live = chain < ws.n_chains;
+            const int slot = ctile * TC_CHAINS + row;
+            const bool live = slot < gm.n_act;
+            const int chain = live ? ws.chain_of_slot[slot] : 0;
             int sel = 0;
-            if (live && ws.st) { live = ws.st[chain].phase <= B2_PHASE_HMC; sel = ws.st[chain].sel; }
+            if (live && ws.st) sel = ws.st[chain].sel;
             const float* q = (sel ? ws.qB : ws.qA) + (size_t)(live ? chain : 0) * ws.ld;
             uint32_t qh[16], ql[16];
 #pragma unroll
@@ -405,8 +442,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
         // the slab's gradient tile: G[chain row][128 features] -> global partials (32 columns per group)
         mbar_wait(g_full, 0, ws.err, 8);
         tc_fence_after();
-        const int chain = ctile * TC_CHAINS + row;
-        float* gout = ws.gpart + ((size_t)split * ws.c_pad + chain) * TC_KP + 32 * cg;
+        const int slot = ctile * TC_CHAINS + row;
+        float* gout = ws.gpart + ((size_t)split * gm.stride + slot) * TC_KP + 32 * cg;
         {
             uint32_t g32[32];
             TC_LD32(tmem + lane_addr + TC_COL_G + 32 * cg, g32);
@@ -418,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
                                 __uint_as_float(g32[4 * i + 2]), __uint_as_float(g32[4 * i + 3]));
         }
         // logp partial of this column group; the finalize kernel adds the TC_EPI_GROUPS partials
-        ws.lpart[((size_t)split * TC_EPI_GROUPS + cg) * ws.c_pad + chain] = logp;
+        ws.lpart[((size_t)split * TC_EPI_GROUPS + cg) * gm.stride + slot] = logp;
     }
     tc_fence_before();
     __syncthreads();
@@ -430,23 +467,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
 
 // fixed-order reduction over slabs + prior + correction for zero-padded rows, for one chain per warp.
 // lane l owns features 4l..4l+3 (one float4 per slab partial).
-__device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int chain, int lane, int K1, double prior_tau,
-                                                    const float* q, float* g) {
+__device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, const TcGeom& gm, int slot, int lane, int K1,
+                                                    double prior_tau, const float* q, float* g) {
     // logp slab partials first, so their round trip overlaps the gradient partials'
-    const int n_lp = ws.splits * TC_EPI_GROUPS;
+    const int n_lp = gm.sp * TC_EPI_GROUPS;
     double lpv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        lpv[j] = (lane + 32 * j < n_lp) ? __ldcg(ws.lpart + (size_t)(lane + 32 * j) * ws.c_pad + chain) : 0.0;
+        lpv[j] = (lane + 32 * j < n_lp) ? __ldcg(ws.lpart + (size_t)(lane + 32 * j) * gm.stride + slot) : 0.0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* gp = reinterpret_cast<const float4*>(ws.gpart + (size_t)chain * TC_KP) + lane;
-    const size_t stride4 = (size_t)ws.c_pad * TC_KP / 4;
+    const float4* gp = reinterpret_cast<const float4*>(ws.gpart + (size_t)slot * TC_KP) + lane;
+    const size_t stride4 = (size_t)gm.stride * TC_KP / 4;
     // all slab partials of this lane in flight at once (one L2 round trip), then a fixed-order sum
-    for (int sp0 = 0; sp0 < ws.splits; sp0 += 24) {
+    for (int sp0 = 0; sp0 < gm.sp; sp0 += 24) {
         float4 v[24];
 #pragma unroll
         for (int j = 0; j < 24; ++j)
-            v[j] = (sp0 + j < ws.splits) ? __ldcg(gp + (size_t)(sp0 + j) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = (sp0 + j < gm.sp) ? __ldcg(gp + (size_t)(sp0 + j) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 24; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
     }
@@ -467,7 +504,7 @@ __device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, int c
         }
     }
     double lp = (lpv[0] + lpv[1]) + (lpv[2] + lpv[3]);
-    for (int sp = lane + 128; sp < n_lp; sp += 32) lp += ws.lpart[(size_t)sp * ws.c_pad + chain];
+    for (int sp = lane + 128; sp < n_lp; sp += 32) lp += ws.lpart[(size_t)sp * gm.stride + slot];
     for (int o = 16; o > 0; o >>= 1) {
         prior += __shfl_xor_sync(0xffffffffu, prior, o);
         lp += __shfl_xor_sync(0xffffffffu, lp, o);
@@ -488,7 +525,8 @@ __global__ void k_glm_tc_finalize(TcWorkspace ws, int n_chains, int K1, double p
     }
     const float* q = (sel ? qB : qA) + (size_t)chain * ld;
     float* g = (sel ? gB : gA) + (size_t)chain * ld;
-    const double lp = tc_finalize_chain(ws, chain, lane, K1, prior_tau, q, g);
+    const TcGeom gm = tc_geom(ws);
+    const double lp = tc_finalize_chain(ws, gm, ws.slot_of_chain[chain], lane, K1, prior_tau, q, g);
     if (lane == 0) logp[chain] = lp;
 }
 
@@ -534,11 +572,19 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
     B2_STAMP(w, c, s, 1);
     const float* q = w.V(B2_V_QE0 + s.sel, c);
     float* gr = w.V(B2_V_GE0 + s.sel, c);
-    const double lp = tc_finalize_chain(ws, c, g.lane(), K1, prior_tau, q, gr);
+    const TcGeom gm = tc_geom(ws);
+    const double lp = tc_finalize_chain(ws, gm, ws.slot_of_chain[c], g.lane(), K1, prior_tau, q, gr);
     __syncwarp();
     B2_STAMP(w, c, s, 2);
-    b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
-    if (g.lane() == 0) w.st[c] = s;
+    const bool active = b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
+    if (g.lane() == 0) {
+        w.st[c] = s;
+        if (active) {                                  // claim a slot in the next step's dense chain tiles
+            const int ns = atomicAdd(ws.counters + (ws.parity ^ 1), 1);
+            ws.chain_of_slot[ns] = c;
+            ws.slot_of_chain[c] = ns;
+        }
+    }
     __syncwarp();
     {   // write the hot slots back (the likelihood kernel and the next launch read them from HBM/L2)
         const int lane = threadIdx.x & 31;
@@ -573,14 +619,21 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     w.n_pad_rows = w.n_tiles * TC_OBS - N;
     w.chain_tiles = (e->C + TC_CHAINS - 1) / TC_CHAINS;
     w.c_pad = w.chain_tiles * TC_CHAINS;
+    // fixed grid: a whole number of slabs per chain tile when every tile is live, one CTA per SM at most
     int splits = e->sm_count / w.chain_tiles;
     if (splits < 1) splits = 1;
     if (splits > w.n_tiles) splits = w.n_tiles;
     w.tiles_per_split = (w.n_tiles + splits - 1) / splits;
     w.splits = (w.n_tiles + w.tiles_per_split - 1) / w.tiles_per_split;
+    w.grid_ctas = w.chain_tiles * w.splits;
+    w.parity = 0;
+    B2_CUDA_OK(cudaMalloc(&w.counters, 2 * sizeof(int)));
+    B2_CUDA_OK(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int), stream));
+    B2_CUDA_OK(cudaMalloc(&w.chain_of_slot, (size_t)w.c_pad * sizeof(int)));
+    B2_CUDA_OK(cudaMalloc(&w.slot_of_chain, (size_t)w.c_pad * sizeof(int)));
     B2_CUDA_OK(cudaMalloc(&w.xt, (size_t)w.n_tiles * TC_STAGE_DATA));
-    B2_CUDA_OK(cudaMalloc(&w.gpart, (size_t)w.splits * w.c_pad * TC_KP * sizeof(float)));
-    B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)w.splits * TC_EPI_GROUPS * w.c_pad * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&w.gpart, (size_t)(w.grid_ctas + w.chain_tiles) * TC_CHAINS * TC_KP * sizeof(float)));
+    B2_CUDA_OK(cudaMalloc(&w.lpart, (size_t)(w.grid_ctas + w.chain_tiles) * TC_EPI_GROUPS * TC_CHAINS * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&w.err, sizeof(int)));
     w.dbg = nullptr;
     if (getenv("B2_TC_TIMELINE")) {
@@ -600,7 +653,7 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
 void b2_glm_tc_release(b2_engine* e) {
     if (!e->glm_tc) return;
     TcHostState* hs = (TcHostState*)e->glm_tc;
-    cudaFree(hs->ws.dbg); cudaFree(hs->ws.xt); cudaFree(hs->ws.gpart); cudaFree(hs->ws.lpart); cudaFree(hs->ws.err);
+    cudaFree(hs->ws.dbg); cudaFree(hs->ws.xt); cudaFree(hs->ws.counters); cudaFree(hs->ws.chain_of_slot); cudaFree(hs->ws.slot_of_chain); cudaFree(hs->ws.gpart); cudaFree(hs->ws.lpart); cudaFree(hs->ws.err);
     delete hs;
     e->glm_tc = nullptr;
 }
@@ -617,12 +670,18 @@ int b2_glm_tc_pack(b2_engine* e, const float* qA, const float* qB, int ld, const
     if (rc) return rc;
     TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
     w.qA = qA; w.qB = qB; w.ld = ld; w.st = st; w.n_chains = n; w.K1 = e->md.G + 1;
+    // dense slot <-> chain maps for the first launch; afterwards k_glm_tc_post maintains them
+    B2_CUDA_OK(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int), stream));
+    w.parity = 0;
+    k_glm_tc_compact<<<(n + 255) / 256, 256, 0, stream>>>(w, st, n);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 1;
     return 0;
 }
 
 int b2_glm_tc_main(b2_engine* e, cudaStream_t stream) {
     TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
-    k_glm_tc_main<<<dim3(w.chain_tiles, w.splits), TC_THREADS, TC_SMEM_BYTES, stream>>>(w);
+    k_glm_tc_main<<<w.grid_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(w);
     e->launches += 1;
     return 0;
 }
@@ -653,6 +712,7 @@ int b2_glm_tc_post(b2_engine* e, const void* view_f32, cudaStream_t stream) {
     k_glm_tc_post<<<(e->C + 3) / 4, 128, 0, stream>>>(w, v, e->md.G + 1, e->md.hp[0]);
     B2_CUDA_OK(cudaGetLastError());
     e->launches += 1;
+    w.parity ^= 1;                                 // the next step reads the counter this launch filled
     return 0;
 }
 
