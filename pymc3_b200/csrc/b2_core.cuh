@@ -541,6 +541,11 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const bool turning = b2_uturn<T, G>(g, w.D, var, f1, l1, s1, f2, l2, s2, k > 0, s1, l1);
             if (turning) { s.turned = 1; break; }
             const double ls1 = w.LV(c, 0, b1);
+            const double la1 = w.LV(c, 1, b1);
+            // Every lane of the group executes this read-modify-write redundantly; all of them must have
+            // read the old level scalars before any lane stores the merged ones (warps of a block group
+            // run out of step, and a late reader would fold the sub-tree in twice).
+            g.sync();
             const double ls = b2_logaddexp<T>(ls1, ls2);
             const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_MERGE, (uint32_t)s.depth,
                                         ((uint32_t)(k + 1) << 16) | (uint32_t)n);
@@ -550,7 +555,7 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
                 w.LV(c, 2, b1) = en2; w.LV(c, 3, b1) = lp2;
             }
             w.LV(c, 0, b1) = ls;
-            w.LV(c, 1, b1) = b2_logaddexp<T>(w.LV(c, 1, b1), la2);
+            w.LV(c, 1, b1) = b2_logaddexp<T>(la1, la2);
         }
         if (s.turned) {
             s.depth += 1;

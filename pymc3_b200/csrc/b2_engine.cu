@@ -100,9 +100,22 @@ __global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w, int 
     if (g.lane() == 0) w.st[c] = s;
 }
 
+// hot != null: shared memory for this chain's B2_V_STACK0 hot vector slots (B2View::hot), loaded once,
+// written back when the chain's run ends -- the persistent kernel then touches HBM/L2 only for the stack
+// buffers, the Welford windows and the trace.
 template <typename T, typename G>
-__device__ __forceinline__ void persistent_body(const G& g, const B2View<T>& w, const B2ModelData& m, int c) {
+__device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const B2ModelData& m, int c, T* hot) {
     B2ChainState s = w.st[c];
+    if (s.phase == B2_PHASE_FAILED || (s.phase == B2_PHASE_DONE && s.iter >= w.iter_end)) return;
+    if (hot) {
+        for (int slot = 0; slot < B2_V_STACK0; ++slot) {
+            const T* src = w.Vglobal(slot, c);
+            T* dst = hot + (size_t)slot * w.Dp;
+            for (int i = g.lane(); i < w.Dp; i += G::NT) dst[i] = src[i];
+        }
+        g.sync();
+        w.hot = hot;
+    }
     if (s.phase == B2_PHASE_DONE && s.iter < w.iter_end) {   // continuation run
         s.phase = B2_PHASE_RESUME;
         b2_advance<T, G>(g, w, c, s, 0.0);
@@ -116,23 +129,33 @@ __device__ __forceinline__ void persistent_body(const G& g, const B2View<T>& w, 
         g.sync();
         active = b2_advance<T, G>(g, w, c, s, lp);
     }
+    if (hot) {
+        g.sync();
+        for (int slot = 0; slot < B2_V_STACK0; ++slot) {
+            T* dst = w.Vglobal(slot, c);
+            const T* src = hot + (size_t)slot * w.Dp;
+            for (int i = g.lane(); i < w.Dp; i += G::NT) dst[i] = src[i];
+        }
+    }
     if (g.lane() == 0) w.st[c] = s;
 }
 
 template <typename T>
-__global__ void k_persistent_warp(B2View<T> w, B2ModelData m) {
+__global__ void k_persistent_warp(B2View<T> w, B2ModelData m, int hot_elems) {
+    extern __shared__ __align__(16) unsigned char hot_raw[];
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= w.C) return;
     B2WarpGroup g;
-    persistent_body<T, B2WarpGroup>(g, w, m, c);
+    persistent_body<T, B2WarpGroup>(g, w, m, c, hot_elems ? reinterpret_cast<T*>(hot_raw) + (size_t)(threadIdx.x >> 5) * hot_elems : (T*)0);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(B2_BLOCK_NT) k_persistent_block(B2View<T> w, B2ModelData m) {
+__global__ void __launch_bounds__(B2_BLOCK_NT) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems) {
+    extern __shared__ __align__(16) unsigned char hot_raw[];
     __shared__ double red[8 * (B2_BLOCK_NT / 32)];
     B2BlockGroup<B2_BLOCK_NT> g;
     g.red = red;
-    persistent_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, m, blockIdx.x);
+    persistent_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, m, blockIdx.x, hot_elems ? reinterpret_cast<T*>(hot_raw) : (T*)0);
 }
 
 __global__ void k_count_active(const B2ChainState* st, int C, int* out) {
@@ -398,8 +421,16 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
     const bool blk = use_block_group(e);
     const int nb_warp = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
     if (mode == B2_EXEC_PERSISTENT) {
-        if (blk) k_persistent_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, e->md);
-        else k_persistent_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, e->md);
+        // shared-memory residency of each chain's hot vector slots when it fits (11 * Dp elements per chain)
+        int hot_elems = B2_V_STACK0 * e->Dp;
+        size_t hot_bytes = (size_t)hot_elems * sizeof(T) * (blk ? 1 : B2_WARPS_PER_BLOCK);
+        if (hot_bytes > (size_t)200 * 1024) { hot_elems = 0; hot_bytes = 0; }
+        if (hot_bytes > 48 * 1024) {
+            if (blk) B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_block<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
+            else B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
+        }
+        if (blk) k_persistent_block<T><<<e->C, B2_BLOCK_NT, hot_bytes, s>>>(w, e->md, hot_elems);
+        else k_persistent_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, hot_bytes, s>>>(w, e->md, hot_elems);
         e->launches += 1;
         B2_CUDA_OK(cudaGetLastError());
         B2_CUDA_OK(cudaStreamSynchronize(s));

@@ -45,6 +45,12 @@ struct B2ModelData {
 #define B2_LOG_PI 1.1447298858494001741434273513531
 #define B2_LOG_2 0.693147180559945309417232121458
 
+// element-wise transcendentals in the vector dtype (fp32 production build: float versions)
+B2_HD float b2_exp_t(float x) { return expf(x); }
+B2_HD double b2_exp_t(double x) { return exp(x); }
+B2_HD float b2_log1p_t(float x) { return log1pf(x); }
+B2_HD double b2_log1p_t(double x) { return log1p(x); }
+
 B2_HD double b2_digamma(double x) {
     double r = 0.0;
     while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
@@ -211,8 +217,8 @@ B2_HD double b2_eval_stoch_vol(const G& g, const B2ModelData& m, const T* q, T* 
         }
         if (i + 1 < Tn) gv += (vol[i + 1] - vi) * (T)inv_s2;
         const double r = m.aux0[i];
-        const T z = (T)exp(-2.0 * (double)vi) * (T)(r * r / nu);        // lam r^2 / nu
-        const T l1 = (T)log1p((double)z);
+        const T z = b2_exp_t((T)-2 * vi) * (T)(r * r / nu);             // lam r^2 / nu
+        const T l1 = b2_log1p_t(z);
         const T zr = z / ((T)1 + z);
         acc[0] += (double)(-vi - (T)hnu1 * l1);                        // 0.5 log(lam) = -vol
         acc[2] += (double)(-(T)0.5 * l1 + (T)hnu1 * zr / (T)nu);
