@@ -97,6 +97,16 @@ def make_workload(name, args):
     raise SystemExit("unknown workload %r" % name)
 
 
+# timing rule: say how the timed iterations avoid measuring a warm-L2 replay of identical work
+L2_NOTES = {
+    "c1": "one persistent launch per step; state lives in shared memory, nothing to replay",
+    "c2": "pre-tiled X (51 MB bf16 hi/lo) is re-read from HBM every leapfrog (ncu: 52 MB DRAM traffic per launch); "
+          "positions, gradients and residuals change every launch",
+    "c3": "observations (6 MB) stay L2-resident by design; the chains' positions change every launch",
+    "c4": "one persistent launch per step; hot state in shared memory, tree stack (0.5 GB for 512 chains) > L2",
+}
+
+
 def start_points(ndim, chains, first_chain):
     """test point + U(-1, 1), keyed by global chain id (sampling.py:1920-1926)."""
     out = np.empty((chains, ndim))
@@ -282,13 +292,26 @@ def run_b200(args):
     ess_info = None
     if not args.skip_ess and total - tune >= 100:
         q = trace["q"][tune:]                                              # [draws, C, D]
-        q = q.permute(1, 0, 2).contiguous().cpu().numpy().astype("f8")      # [C, draws, D]
-        vals = model.expand(q)
-        ess_vec = np.concatenate([np.ravel(b2stats.ess(v)) for v in vals.values()])
+        ess_note = "every scalar of every free and back-transformed variable"
+        if q.shape[2] > 512:
+            # rank-normalised ESS of ~3000 scalars x 512k draws takes minutes on the host: the hyper-parameters
+            # (first and last 8 columns) plus 112 evenly spaced latent states; bulk ESS is rank based, so the
+            # elementwise monotone back-transforms do not change it
+            Dq = q.shape[2]
+            cols = np.unique(np.concatenate([np.arange(8), np.arange(Dq - 8, Dq),
+                                             np.linspace(8, Dq - 9, 112).astype(int)]))
+            qs = q[:, :, torch.as_tensor(cols, device=q.device)]
+            qs = qs.permute(1, 0, 2).contiguous().cpu().numpy().astype("f8")
+            ess_vec = np.ravel(b2stats.ess(qs))
+            ess_note = "%d of %d free scalars (first/last 8 + 112 evenly spaced)" % (len(cols), Dq)
+        else:
+            q = q.permute(1, 0, 2).contiguous().cpu().numpy().astype("f8")  # [C, draws, D]
+            vals = model.expand(q)
+            ess_vec = np.concatenate([np.ravel(b2stats.ess(v)) for v in vals.values()])
         ess_t = torch.tensor(ess_vec, dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ess_t, op=dist.ReduceOp.SUM)                    # independent chain sets add
-        ess_info = {"min_bulk_ess": float(ess_t.min().item()), "n_scalars": int(ess_t.numel())}
+        ess_info = {"min_bulk_ess": float(ess_t.min().item()), "n_scalars": int(ess_t.numel()), "over": ess_note}
     del trace
 
     # ---- pass B: end to end -- every step uploads its inputs from pinned host memory and reads
@@ -364,7 +387,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "chains_per_gpu": chains, "chains_total": chains * world,
                    "iters_per_step": ips, "tune": tune, "draws": total - tune, "sampler": "NUTS target_accept=0.8",
-                   "l2": "X (40 MB fp32) is re-read from L2/HBM every leapfrog; inputs change every launch",
+                   "l2": L2_NOTES.get(args.workload, "inputs change every launch"),
                    "grad_evals_counted": "sum of tree_size (leapfrogs) in the timed steps"},
         # whole sampling job incl. tuning (mirrors benchmarks/benchmarks/benchmarks.py:163-169)
         "min_bulk_ess_per_sec": (ess_info["min_bulk_ess"] / (t_timed + float(t_vec[2].item()))

@@ -186,7 +186,7 @@ __device__ __forceinline__ float tc_rcp(float x) { float y; asm("rcp.approx.ftz.
 // instruction descriptors (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16
 #define TC_IDESC_BASE ((1u << 4) | (1u << 7) | (1u << 10))
 #define TC_IDESC_G1 (TC_IDESC_BASE | ((TC_OBS >> 3) << 17) | ((TC_CHAINS >> 4) << 24))               // N=64,  K-major B
-#define TC_IDESC_G2 (TC_IDESC_BASE | (1u << 16) | ((TC_KP >> 3) << 17) | ((TC_CHAINS >> 4) << 24))   // N=128, MN-major B
+// GEMM2 (MN-major B, bit 16) takes its N from the feature count at run time: see the GEMM2 issuer
 
 struct TcGeom { int n_act, nt, sp, tps, stride; };     // active chains, live tiles, row slabs, tiles per slab, slots
 __device__ __forceinline__ TcGeom tc_geom(const TcWorkspace& ws) {
@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
         // (timeline r1: 2460 cycles of issuer time per tile for 1536 cycles of tensor work).
         mbar_wait(q_full, 0, ws.err, 2);                           // epilogue warps have written Q into TMEM
         tc_fence_after();
+        const int ks = (ws.K1 + 15) >> 4;                          // K steps that hold real features (7 of 8 at D+1 = 101)
         for (int t = 0; t < T; ++t) {
             const int s = t % TC_STAGES, b = t & 1;
             if (lane == 0) TC_STAMP(0, t);
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
                     const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
 #pragma unroll
                     for (int j = 0; j < TC_KP / 16; ++j) {
+                        if (j >= ks) break;                            // all-zero padding columns: no tensor work spent on them
                         const uint32_t koff = (j & 3) * 32;
                         const uint64_t bd = make_desc(xa + (j >> 2) * (TC_OBS * 128) + koff, 16, 1024);
                         mma_ts(d, qa + j * 8, bd, TC_IDESC_G1, acc);   // A from TMEM: no 4 KB smem read per MMA
@@ -305,6 +307,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
         }
     } else if (warp == 3) {
         // ===== GEMM2 issuer: G += R(u) . Xtile(u), three split passes; releases the X stage and the R buffer
+        // N = features rounded up to 16 (UMMA N granularity at M = 128): 112 instead of 128 at D+1 = 101
+        const uint32_t n2 = (uint32_t)((ws.K1 + 15) & ~15);
+        const uint32_t idesc_g2 = TC_IDESC_BASE | (1u << 16) | ((n2 >> 3) << 17) | ((TC_CHAINS >> 4) << 24);
         for (int u = 0; u < T; ++u) {
             const int s = u % TC_STAGES, b = u & 1;
             if (lane == 0) TC_STAMP(2, u);
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_glm_tc_main(TcWorkspace ws) {
                     for (int j = 0; j < TC_OBS / 16; ++j) {
                         // MN-major B: 2 feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
                         const uint64_t bd = make_desc(xa + j * 2048, TC_OBS * 128, 1024);
-                        mma_ts(d, pa + j * 8, bd, TC_IDESC_G2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+                        mma_ts(d, pa + j * 8, bd, idesc_g2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
                     }
                 }
                 tc_commit(x_empty + s);

@@ -239,6 +239,26 @@ def test_block_per_chain_group_on_full_stochastic_volatility(exec_mode):
         assert (st["depth"] == out["depth"][:, c]).all()
         assert (st["tree_size"] == out["tree_size"][:, c]).all()
         assert np.abs(qs - out["q"][:, c]).max() < 1e-7
+        assert np.abs(st["mean_tree_accept"] - out["mean_tree_accept"][:, c]).max() < 1e-7
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_block_per_chain_accept_statistic_stays_a_probability(dtype):
+    """Regression: the warps of a block-per-chain group once raced on the per-level log-size /
+    log-accept-sum scalars (nuts.py:369-380 executed redundantly by every lane), which folded
+    sub-trees in twice, pushed mean_tree_accept past 1 and blew up dual averaging.  Deep trees
+    (early_max_treedepth 8) with adaptation on: the statistic is a probability and no chain stalls."""
+    from pymc3_b200 import model as pm
+    model = pm.StochVol()
+    C, D, n = 16, 2907, 160
+    q0 = np.random.default_rng(10).uniform(-1, 1, size=(C, D))
+    out = _run_engine(model, q0, np.arange(C) + 900, n, n, _capi.B2_NUTS, dtype, _capi.B2_EXEC_PERSISTENT)
+    acc = out["mean_tree_accept"]
+    assert np.isfinite(acc).all() and acc.max() <= 1.0 + 1e-5 and acc.min() >= 0.0
+    assert all(r.phase == _capi.PHASE_DONE for r in out["reports"])
+    assert out["depth"].max() >= 7
+    assert 0.6 < acc[-60:].mean() < 0.95
+    assert out["step_size"][-1].max() < 1.0
 
 
 @pytest.mark.parametrize("exec_mode", [_capi.B2_EXEC_PERSISTENT, _capi.B2_EXEC_LOCKSTEP])
