@@ -20,12 +20,18 @@ eng.run(_capi.B2_NUTS, 400, 300, opts)
 out = np.zeros((4096, 16), dtype=np.int64)
 rc = _capi.load_library().b2_debug_post_timeline(eng.handle, out.ctypes.data_as(C.c_void_p))
 assert rc == 0
-rows = out[(out[:, 0] > 0) & (out[:, 8] > 0)]
+rows = out[(out[:, 0] > 0) & (out[:, 8] > out[:, 0]) & (out[:, 7] > 0)]
 names = ["state load", "finalize", "finish leaf/merges", "top merge", "end transition", "begin transition", "begin doubling+prepare", "state store"]
 d = np.diff(rows[:, :9], axis=1)
-kinds = {"plain leaf": (d[:, 3] < 50) & (d[:, 4] < 50), "transition end": d[:, 4] > 50}
-for k, m in kinds.items():
+tot = rows[:, 8] - rows[:, 0]
+ended = rows[:, 12] != rows[:, 11]
+nm = rows[:, 10]
+print("%-28s %5s %8s %8s   %s" % ("kind", "n", "mean", "p95", " | ".join(names)))
+for label, m in [("leaf, 0 merges", (nm == 0) & ~ended), ("leaf, 1-2 merges", (nm >= 1) & (nm <= 2) & ~ended),
+                 ("leaf, 3-5 merges", (nm >= 3) & (nm <= 5) & ~ended), ("leaf, 6+ merges", (nm >= 6) & ~ended),
+                 ("transition end (tuning)", ended & (rows[:, 11] < 300)), ("transition end (sampling)", ended & (rows[:, 11] >= 300))]:
     if m.sum() == 0:
         continue
-    print("%-15s n=%4d total %7.0f cycles:" % (k, m.sum(), rows[m, 8].mean() - rows[m, 0].mean()),
-          ", ".join("%s %.0f" % (n, v) for n, v in zip(names, d[m].mean(axis=0))))
+    print("%-28s %5d %8.0f %8.0f   %s" % (label, m.sum(), tot[m].mean(), np.percentile(tot[m], 95),
+                                         " | ".join("%6.0f" % v for v in d[m].mean(axis=0))))
+print("all rows: mean %.0f p50 %.0f p95 %.0f p99 %.0f max %.0f cycles" % (tot.mean(), np.percentile(tot, 50), np.percentile(tot, 95), np.percentile(tot, 99), tot.max()))

@@ -108,11 +108,22 @@ struct B2View {
         if (lv_hot) return lv_hot[which * B2_MAX_LEVELS + buf];
         return lv[((size_t)c * 4 + which) * B2_MAX_LEVELS + buf];
     }
-    B2_HD T* S(int buf, int which, int c) const { return V(B2_V_STACK0 + buf * B2_S_NVEC + which, c); }
+    // Optional on-chip copy of SOME of this chain's stack buffers (the ones the pending leaf will merge):
+    // [n_staged][B2_S_NVEC][Dp]; bit `buf` of stk_mask says buffer `buf` is staged, its position is the
+    // 4-bit field `buf` of stk_idx.  Filled and written back by the kernel that sets it.
+    T* stk_hot;
+    unsigned stk_mask;
+    unsigned long long stk_idx;
+    B2_HD T* S(int buf, int which, int c) const {
+        if (stk_hot && ((stk_mask >> buf) & 1u))
+            return stk_hot + ((size_t)((stk_idx >> (4 * buf)) & 0xFull) * B2_S_NVEC + which) * Dp;
+        return V(B2_V_STACK0 + buf * B2_S_NVEC + which, c);
+    }
 };
 
 #if defined(__CUDA_ARCH__)
-#define B2_STAMP(w, c, s, k) do { if ((w).dbg && (c) == 0) (w).dbg[((s).n_grad & 4095) * 16 + (k)] = clock64(); } while (0)
+// (stamps 3.. are taken after the leapfrog counter moved on: same row as stamps 0..2 of this launch)
+#define B2_STAMP(w, c, s, k) do { if ((w).dbg && (c) == 0) (w).dbg[(((s).n_grad - ((k) >= 3 ? 1 : 0)) & 4095) * 16 + (k)] = clock64(); } while (0)
 #else
 #define B2_STAMP(w, c, s, k) do { } while (0)
 #endif
@@ -163,11 +174,21 @@ struct B2BlockGroup {                      // block per chain (large D)
             for (int k = 0; k < K; ++k) red[k * NW + w] = x[k];
         }
         __syncthreads();
+        if (NW <= 8) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double s = 0.0;
-            for (int j = 0; j < NW; ++j) s += red[k * NW + j];   // same order in every thread
-            x[k] = s;
+            for (int k = 0; k < K; ++k) {
+                double s = 0.0;
+                for (int j = 0; j < NW; ++j) s += red[k * NW + j];   // same order in every thread
+                x[k] = s;
+            }
+        } else {                           // 16 or 32 warps: one more butterfly, identical in every warp
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double s = l < NW ? red[k * NW + l] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                x[k] = s;
+            }
         }
     }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -407,17 +428,39 @@ B2_HD int b2_end_transition(const G& g, const B2View<T>& w, int c, B2ChainState&
         double* b2 = w.wv_m2 + ((size_t)b * w.C + c) * w.Dp;
         const double nf = s.wv_count[f] + 1.0, nb = s.wv_count[b] + 1.0;
         const bool swap = (s.n_seen > 0) && (s.n_seen % s.window == 0);
-        for (int i = g.lane(); i < w.D; i += G::NT) {
-            const double x = (double)pq[i];
-            double od = x - fm[i];
-            const double m = fm[i] + od / nf;
-            const double r = f2[i] + od * (x - m);
-            var[i] = (T)(r / nf);
-            od = x - bm[i];
-            const double m_b = bm[i] + od / nb;
-            const double r_b = b2[i] + od * (x - m_b);
-            if (swap) { fm[i] = 0.0; f2[i] = 0.0; } else { fm[i] = m; f2[i] = r; }
-            bm[i] = m_b; b2[i] = r_b;
+        // four components per pass, loads first and stores last: 16 loads in flight and 12 independent fp64
+        // divisions instead of one load round trip and three dependent divisions per component (a chain that
+        // ends its transition is the critical path of a lock-step launch)
+        for (int i0 = g.lane(); i0 < w.D; i0 += 4 * G::NT) {
+            double x[4], mf[4], rf[4], mb[4], rb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * G::NT;
+                const bool ok = i < w.D;
+                x[u] = ok ? (double)pq[i] : 0.0;
+                mf[u] = ok ? fm[i] : 0.0; rf[u] = ok ? f2[i] : 0.0;
+                mb[u] = ok ? bm[i] : 0.0; rb[u] = ok ? b2[i] : 0.0;
+            }
+            T vnew[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double od = x[u] - mf[u];
+                mf[u] = mf[u] + od / nf;
+                rf[u] = rf[u] + od * (x[u] - mf[u]);
+                vnew[u] = (T)(rf[u] / nf);
+                od = x[u] - mb[u];
+                mb[u] = mb[u] + od / nb;
+                rb[u] = rb[u] + od * (x[u] - mb[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * G::NT;
+                if (i < w.D) {
+                    var[i] = vnew[u];
+                    if (swap) { fm[i] = 0.0; f2[i] = 0.0; } else { fm[i] = mf[u]; f2[i] = rf[u]; }
+                    bm[i] = mb[u]; b2[i] = rb[u];
+                }
+            }
         }
         s.wv_count[f] = nf; s.wv_count[b] = nb;
         if (swap) { s.wv_count[f] = 0.0; s.fg_sel = b; }   // background becomes foreground

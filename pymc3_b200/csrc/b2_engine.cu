@@ -149,13 +149,29 @@ __global__ void k_persistent_warp(B2View<T> w, B2ModelData m, int hot_elems) {
     persistent_body<T, B2WarpGroup>(g, w, m, c, hot_elems ? reinterpret_cast<T*>(hot_raw) + (size_t)(threadIdx.x >> 5) * hot_elems : (T*)0);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(B2_BLOCK_NT) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems) {
+// NT threads own one chain.  With the hot slots in shared memory only one block fits an SM at D ~ 3000, so the
+// block itself has to bring enough warps to hide latency: NT is picked per run (persistent_block_threads).
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems) {
     extern __shared__ __align__(16) unsigned char hot_raw[];
-    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
-    B2BlockGroup<B2_BLOCK_NT> g;
+    __shared__ double red[8 * (NT / 32)];
+    B2BlockGroup<NT> g;
     g.red = red;
-    persistent_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, m, blockIdx.x, hot_elems ? reinterpret_cast<T*>(hot_raw) : (T*)0);
+    persistent_body<T, B2BlockGroup<NT>>(g, w, m, blockIdx.x, hot_elems ? reinterpret_cast<T*>(hot_raw) : (T*)0);
+}
+
+template <typename T, int NT>
+static int launch_persistent_block(b2_engine* e, const B2View<T>& w, int hot_elems, size_t hot_bytes, cudaStream_t s) {
+    if (hot_bytes > 48 * 1024)
+        B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_block<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
+    k_persistent_block<T, NT><<<e->C, NT, hot_bytes, s>>>(w, e->md, hot_elems);
+    return 0;
+}
+
+static int persistent_block_threads(const b2_engine* e) {
+    const char* env = getenv("B2_PBLOCK_NT");
+    if (env) { const int v = atoi(env); if (v == 256 || v == 512 || v == 1024) return v; }
+    return e->D >= 2048 ? 512 : 256;
 }
 
 __global__ void k_count_active(const B2ChainState* st, int C, int* out) {
@@ -425,11 +441,15 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         int hot_elems = B2_V_STACK0 * e->Dp;
         size_t hot_bytes = (size_t)hot_elems * sizeof(T) * (blk ? 1 : B2_WARPS_PER_BLOCK);
         if (hot_bytes > (size_t)200 * 1024) { hot_elems = 0; hot_bytes = 0; }
-        if (hot_bytes > 48 * 1024) {
-            if (blk) B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_block<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
-            else B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
+        if (hot_bytes > 48 * 1024 && !blk)
+            B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
+        if (blk) {
+            const int nt = persistent_block_threads(e);
+            int rc = nt == 1024 ? launch_persistent_block<T, 1024>(e, w, hot_elems, hot_bytes, s)
+                   : nt == 512  ? launch_persistent_block<T, 512>(e, w, hot_elems, hot_bytes, s)
+                                : launch_persistent_block<T, 256>(e, w, hot_elems, hot_bytes, s);
+            if (rc) return rc;
         }
-        if (blk) k_persistent_block<T><<<e->C, B2_BLOCK_NT, hot_bytes, s>>>(w, e->md, hot_elems);
         else k_persistent_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, hot_bytes, s>>>(w, e->md, hot_elems);
         e->launches += 1;
         B2_CUDA_OK(cudaGetLastError());

@@ -28,6 +28,7 @@
 
 #define TC_CHAINS 128                 // MMA M
 #define TC_OBS 64                     // observations per tile (GEMM1 N, GEMM2 K)
+#define TC_POST_STAGE 6               // stack buffers k_glm_tc_post stages per chain (merge levels 0..5)
 #define TC_KP 128                     // padded feature count (GEMM1 K, GEMM2 N)
 #define TC_STAGES 6
 #define TC_XPART_BYTES (TC_OBS * TC_KP * 2)            // 16384: one of {hi, lo}, two 64-column atoms
@@ -546,53 +547,81 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
     w.dbg = ws.dbg ? ws.dbg + 48 * TC_DBG_TILES : nullptr;          // post-kernel stamps live behind the main kernel's
     const long long t_start = clock64();
     __shared__ __align__(16) float hot_s[4][B2_V_STACK0 * 128];
-    // stage this chain's 11 hot vector slots in shared memory: issued together with the state load
-    float* hot = hot_s[threadIdx.x >> 5];
-    {
-        const int lane = threadIdx.x & 31;
-        float4 tmp[B2_V_STACK0];
-#pragma unroll
-        for (int slot = 0; slot < B2_V_STACK0; ++slot)
-            tmp[slot] = (4 * lane < w.Dp) ? *reinterpret_cast<const float4*>(w.Vglobal(slot, c) + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int slot = 0; slot < B2_V_STACK0; ++slot)
-            if (4 * lane < w.Dp) *reinterpret_cast<float4*>(hot + slot * w.Dp + 4 * lane) = tmp[slot];
-    }
     __shared__ double lv_s[4][4 * B2_MAX_LEVELS];
+    float* hot = hot_s[threadIdx.x >> 5];
     double* lvh = lv_s[threadIdx.x >> 5];
-    {
-        const int lane = threadIdx.x & 31;
-        const double* src = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
-        const double a0 = src[lane];
-        const double a1 = (lane + 32 < 4 * B2_MAX_LEVELS) ? src[lane + 32] : 0.0;
-        lvh[lane] = a0;
-        if (lane + 32 < 4 * B2_MAX_LEVELS) lvh[lane + 32] = a1;
-    }
+    // Everything this warp needs from global memory is requested before anything is stored to shared memory
+    // (the loads go through generic pointers, so the compiler keeps them behind earlier shared stores):
+    // one round trip for the chain state, its 11 hot vector slots, the level scalars and the slot maps.
+    const int lane0 = threadIdx.x & 31;
+    float4 tmp[B2_V_STACK0];
+#pragma unroll
+    for (int slot = 0; slot < B2_V_STACK0; ++slot)
+        tmp[slot] = (4 * lane0 < w.Dp) ? *reinterpret_cast<const float4*>(w.Vglobal(slot, c) + 4 * lane0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const double* lv_src = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
+    const double lv_a0 = lv_src[lane0];
+    const double lv_a1 = (lane0 + 32 < 4 * B2_MAX_LEVELS) ? lv_src[lane0 + 32] : 0.0;
+    const int my_slot = ws.slot_of_chain[c];
+    const TcGeom gm = tc_geom(ws);
     B2ChainState s = w.st[c];
+#pragma unroll
+    for (int slot = 0; slot < B2_V_STACK0; ++slot)
+        if (4 * lane0 < w.Dp) *reinterpret_cast<float4*>(hot + slot * w.Dp + 4 * lane0) = tmp[slot];
+    lvh[lane0] = lv_a0;
+    if (lane0 + 32 < 4 * B2_MAX_LEVELS) lvh[lane0 + 32] = lv_a1;
     if (!b2_needs_grad(s.phase)) return;
+    // Stack buffers the pending leaf will merge (one per trailing one-bit of its index, nuts.py:347-389 as a
+    // binary counter): fetched with cp.async while the slab reduction below runs, so every merge level works
+    // out of shared memory instead of paying 4-6 dependent L2 round trips (timeline r1: 5-7k cycles per level,
+    // and the kernel lasts as long as its deepest merge chain).
+    extern __shared__ __align__(16) unsigned char post_dyn[];
+    float* stk = reinterpret_cast<float*>(post_dyn) + (size_t)(threadIdx.x >> 5) * TC_POST_STAGE * B2_S_NVEC * w.Dp;
+    int n_merge = 0, n_staged = 0, wb_buf = -1;
+    unsigned stk_mask = 0;
+    unsigned long long stk_idx = 0;
+    if (s.phase == B2_PHASE_TREE) {
+        while ((s.leaf_n >> n_merge) & 1) ++n_merge;
+        n_staged = n_merge < TC_POST_STAGE ? n_merge : TC_POST_STAGE;
+        const int lane = threadIdx.x & 31;
+        for (int k = 0; k < n_staged; ++k) {
+            const int buf = b2_map_get(s.slot_map, k);
+            stk_mask |= 1u << buf;
+            stk_idx |= (unsigned long long)k << (4 * buf);
+            if (4 * lane < w.Dp) {
+#pragma unroll
+                for (int which = 0; which < B2_S_NVEC; ++which) {
+                    const float* src = w.Vglobal(B2_V_STACK0 + buf * B2_S_NVEC + which, c) + 4 * lane;
+                    const uint32_t dst = smem_u32(stk + ((size_t)k * B2_S_NVEC + which) * w.Dp + 4 * lane);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                }
+            }
+        }
+        if (n_staged == n_merge && n_merge > 0) wb_buf = b2_map_get(s.slot_map, n_merge - 1);   // the merged sub-tree ends up here
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     __syncwarp();
     w.hot = hot;
     w.lv_hot = lvh;
-    if (w.dbg && c == 0) w.dbg[(s.n_grad & 4095) * 16 + 0] = t_start;
+    if (w.dbg && c == 0) { w.dbg[(s.n_grad & 4095) * 16 + 0] = t_start; w.dbg[(s.n_grad & 4095) * 16 + 10] = n_merge; w.dbg[(s.n_grad & 4095) * 16 + 11] = s.iter; }
     B2_STAMP(w, c, s, 1);
     const float* q = w.V(B2_V_QE0 + s.sel, c);
     float* gr = w.V(B2_V_GE0 + s.sel, c);
-    const TcGeom gm = tc_geom(ws);
-    const double lp = tc_finalize_chain(ws, gm, ws.slot_of_chain[c], g.lane(), K1, prior_tau, q, gr);
+    const double lp = tc_finalize_chain(ws, gm, my_slot, g.lane(), K1, prior_tau, q, gr);
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
+    if (n_staged > 0) { w.stk_hot = stk; w.stk_mask = stk_mask; w.stk_idx = stk_idx; }
     B2_STAMP(w, c, s, 2);
     const bool active = b2_advance<float, B2WarpGroup>(g, w, c, s, lp);
-    if (g.lane() == 0) {
-        w.st[c] = s;
-        if (active) {                                  // claim a slot in the next step's dense chain tiles
-            const int ns = atomicAdd(ws.counters + (ws.parity ^ 1), 1);
-            ws.chain_of_slot[ns] = c;
-            ws.slot_of_chain[c] = ns;
-        }
-    }
-    __syncwarp();
+    __syncwarp();                                      // lanes wrote element i, read back as float4 rows
     {   // write the hot slots back (the likelihood kernel and the next launch read them from HBM/L2)
         const int lane = threadIdx.x & 31;
+        if (wb_buf >= 0 && 4 * lane < w.Dp) {          // the one staged stack buffer that is still alive
+            const int k = n_merge - 1;
+#pragma unroll
+            for (int which = 0; which < B2_S_NVEC; ++which)
+                *reinterpret_cast<float4*>(w.Vglobal(B2_V_STACK0 + wb_buf * B2_S_NVEC + which, c) + 4 * lane) =
+                    *reinterpret_cast<const float4*>(stk + ((size_t)k * B2_S_NVEC + which) * w.Dp + 4 * lane);
+        }
         double* dst = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
         dst[lane] = lvh[lane];
         if (lane + 32 < 4 * B2_MAX_LEVELS) dst[lane + 32] = lvh[lane + 32];
@@ -602,7 +631,16 @@ __global__ void k_glm_tc_post(TcWorkspace ws, B2View<float> w, int K1, double pr
                 *reinterpret_cast<float4*>(w.Vglobal(slot, c) + 4 * lane) = *reinterpret_cast<const float4*>(hot + slot * w.Dp + 4 * lane);
         }
     }
-    if (w.dbg && c == 0) { __threadfence(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 8] = clock64(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 9] = s.leaf_n * 100 + s.depth; }
+    if (g.lane() == 0) {
+        w.st[c] = s;
+        if (active) {                                  // claim a slot in the next step's dense chain tiles
+            const int ns = atomicAdd(ws.counters + (ws.parity ^ 1), 1);
+            ws.chain_of_slot[ns] = c;
+            ws.slot_of_chain[c] = ns;
+        }
+    }
+    __syncwarp();
+    if (w.dbg && c == 0) { __threadfence(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 8] = clock64(); w.dbg[((s.n_grad - 1) & 4095) * 16 + 9] = s.leaf_n * 100 + s.depth; w.dbg[((s.n_grad - 1) & 4095) * 16 + 12] = s.iter; }
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -649,6 +687,8 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     k_glm_tc_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt, w.n_tiles);
     B2_CUDA_OK(cudaGetLastError());
     B2_CUDA_OK(cudaFuncSetAttribute(k_glm_tc_main, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    B2_CUDA_OK(cudaFuncSetAttribute(k_glm_tc_post, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    4 * TC_POST_STAGE * B2_S_NVEC * TC_KP * (int)sizeof(float)));
     e->launches += 1;
     hs->ready = true;
     e->glm_tc = hs;            // owned by the engine; released in b2_glm_tc_release
@@ -714,7 +754,8 @@ extern "C" int b2_debug_post_timeline(b2_engine* e, long long* host_out) {
 int b2_glm_tc_post(b2_engine* e, const void* view_f32, cudaStream_t stream) {
     TcWorkspace& w = ((TcHostState*)e->glm_tc)->ws;
     const B2View<float>& v = *reinterpret_cast<const B2View<float>*>(view_f32);
-    k_glm_tc_post<<<(e->C + 3) / 4, 128, 0, stream>>>(w, v, e->md.G + 1, e->md.hp[0]);
+    const size_t dyn = (size_t)4 * TC_POST_STAGE * B2_S_NVEC * e->Dp * sizeof(float);
+    k_glm_tc_post<<<(e->C + 3) / 4, 128, dyn, stream>>>(w, v, e->md.G + 1, e->md.hp[0]);
     B2_CUDA_OK(cudaGetLastError());
     e->launches += 1;
     w.parity ^= 1;                                 // the next step reads the counter this launch filled

@@ -205,25 +205,29 @@ B2_HD double b2_eval_stoch_vol(const G& g, const B2ModelData& m, const T* q, T* 
     const double inv_s2 = 1.0 / (s * s);
     const double hnu1 = 0.5 * (nu + 1.0);
     const T* vol = q + 1;
-    // logp terms, sum d^2, sum dnu-part
-    double acc[3] = {0.0, 0.0, 0.0};
+    // logp terms, sum d^2, sum dnu-part: a lane's few elements are summed in the vector dtype, the
+    // cross-lane reduction is always fp64
+    T part[3] = {(T)0, (T)0, (T)0};
+    const T inv_s2_t = (T)inv_s2, inv_nu = (T)(1.0 / nu), hnu1_t = (T)hnu1, nu1_t = (T)(nu + 1.0);
+    const T hnu1_over_nu = (T)(hnu1 / nu);
     for (int i = g.lane(); i < Tn; i += G::NT) {
         const T vi = vol[i];
         T gv = (T)0;
         if (i > 0) {
             const T d = vi - vol[i - 1];
-            acc[1] += (double)(d * d);
-            gv -= d * (T)inv_s2;
+            part[1] += d * d;
+            gv -= d * inv_s2_t;
         }
-        if (i + 1 < Tn) gv += (vol[i + 1] - vi) * (T)inv_s2;
-        const double r = m.aux0[i];
-        const T z = b2_exp_t((T)-2 * vi) * (T)(r * r / nu);             // lam r^2 / nu
+        if (i + 1 < Tn) gv += (vol[i + 1] - vi) * inv_s2_t;
+        const T r = (T)m.aux0[i];
+        const T z = b2_exp_t((T)-2 * vi) * (r * r * inv_nu);           // lam r^2 / nu
         const T l1 = b2_log1p_t(z);
         const T zr = z / ((T)1 + z);
-        acc[0] += (double)(-vi - (T)hnu1 * l1);                        // 0.5 log(lam) = -vol
-        acc[2] += (double)(-(T)0.5 * l1 + (T)hnu1 * zr / (T)nu);
-        grad[1 + i] = gv + ((T)(nu + 1.0) * zr - (T)1);
+        part[0] += -vi - hnu1_t * l1;                                  // 0.5 log(lam) = -vol
+        part[2] += -(T)0.5 * l1 + hnu1_over_nu * zr;
+        grad[1 + i] = gv + (nu1_t * zr - (T)1);
     }
+    double acc[3] = {(double)part[0], (double)part[1], (double)part[2]};
     g.allsum(acc);
     const double n1 = (double)(Tn - 1);
     double lp = (log(m.hp[0]) - m.hp[0] * s + a)                                  // Exp(s|10) + jacobian
