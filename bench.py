@@ -360,15 +360,19 @@ def run_b200(args):
             traffic = json.load(f).get("k_glm_tc_main", {}).get("dram_bytes_per_launch")
     if like_n > 0 and wl["bound"]:
         per_launch_s = like_ms / 1e3 / like_n
+        # units one launch processes = chains still inside a trajectory (the launch skips finished chains and,
+        # on the tensor-core path, compacts the live ones into dense tiles): counted, not assumed
+        units = leap_timed / like_n
         if wl["bound"] == "tensor":
-            ach = wl["flops_per_chain_grad"] * chains / per_launch_s / 1e12
+            ach = wl["flops_per_chain_grad"] * units / per_launch_s / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tflops"], "traffic": traffic}
         else:
-            ach = wl["bytes_per_chain_grad"] * chains / per_launch_s / 1e9
+            ach = wl["bytes_per_chain_grad"] * units / per_launch_s / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": ach / peaks["hbm_gbs"], "traffic": None}
         roofline.update({"kernel": "chain-batched likelihood (logp+dlogp, all chains)", "launches_timed": int(like_n),
+                         "chain_grads_per_launch": units,
                          "avg_launch_us": per_launch_s * 1e6, "kernel_share_of_step": like_ms / dev_ms,
                          "advance_kernel_avg_us": adv_ms * 1e3 / like_n, "advance_share_of_step": adv_ms / dev_ms,
                          "peak_source": peaks["source"]})

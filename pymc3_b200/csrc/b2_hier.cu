@@ -16,23 +16,56 @@
 #define HT_CHAINS 128
 #define HT_TILE 2048
 
+// Launch geometry, derived on the device from the number of chains that still need a gradient: the live
+// chains are packed into dense 128-chain tiles (k_hier_compact) and the fixed grid is re-divided into as many
+// observation slabs per tile as fit, so a launch costs what its live chains cost (early in tuning and at the
+// end of a run most chains wait for a few deep trees).
+struct HierGeom { int n_act, nt, sp, rows_per_split, stride; };
+__device__ __forceinline__ HierGeom hier_geom(const int* cnt, int grid_ctas, int N) {
+    HierGeom g;
+    g.n_act = *cnt;
+    g.nt = (g.n_act + HT_CHAINS - 1) / HT_CHAINS;
+    int sp = g.nt > 0 ? grid_ctas / g.nt : 1;
+    const int max_sp = (N + 255) / 256;
+    if (sp > max_sp) sp = max_sp;
+    if (sp < 1) sp = 1;
+    g.rows_per_split = (N + sp - 1) / sp;
+    g.sp = (N + g.rows_per_split - 1) / g.rows_per_split;
+    g.stride = g.nt * HT_CHAINS;
+    return g;
+}
+
+// slot <-> chain map of the chains that need a gradient (st == null: parity hook, every chain, identity order)
+__global__ void k_hier_compact(const B2ChainState* st, int n_chains, int* cnt, int* chain_of_slot) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    if (!st) { chain_of_slot[c] = c; if (c == 0) *cnt = n_chains; return; }
+    if (st[c].phase > B2_PHASE_HMC) return;
+    chain_of_slot[atomicAdd(cnt, 1)] = c;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(HT_CHAINS)
 k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, const int* __restrict__ grp_off,
-            int N, int NG, const T* qA, const T* qB, int ld, const B2ChainState* st, int n_chains,
-            int rows_per_split, T* __restrict__ part /* [split][2*NG+1][n_chains] */) {
+            int N, int NG, const T* qA, const T* qB, int ld, const B2ChainState* st, const int* cnt,
+            const int* __restrict__ chain_of_slot, T* __restrict__ part /* [split][2*NG+1][stride] */) {
     __shared__ __align__(16) float ys[HT_TILE];
     __shared__ __align__(16) float fs[HT_TILE];     // covariate converted u8 -> float once per tile, not per (chain, obs)
     __shared__ int s_g0;
+    const HierGeom gm = hier_geom(cnt, gridDim.x, N);
+    if ((int)blockIdx.x >= gm.nt * gm.sp) return;
     const int tid = threadIdx.x;
-    const int chain = blockIdx.x * HT_CHAINS + tid;
-    const int split = blockIdx.y;
+    const int ctile = blockIdx.x / gm.sp, split = blockIdx.x % gm.sp;
+    const int slot = ctile * HT_CHAINS + tid;
+    const int rows_per_split = gm.rows_per_split;
     const int row_begin = split * rows_per_split;
     const int row_end = min(N, row_begin + rows_per_split);
-    bool live = chain < n_chains;
+    const bool live = slot < gm.n_act;
+    const int chain = live ? chain_of_slot[slot] : 0;
+    const int n_chains = gm.stride;                  // partials are indexed by slot
     int sel = 0;
-    if (live && st) { live = st[chain].phase <= B2_PHASE_HMC; sel = st[chain].sel; }
-    const T* q = (sel ? qB : qA) + (size_t)(live ? chain : 0) * ld;
+    if (live && st) sel = st[chain].sel;
+    const T* q = (sel ? qB : qA) + (size_t)chain * ld;
     const T mu_a = q[0], mu_b = q[2];
     const T sa = (T)exp((double)q[1]), sb = (T)exp((double)q[3]);
     if (tid == 0) {                                    // first group intersecting the slab
@@ -81,8 +114,8 @@ k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, c
             }
             if (t0 + i == g_end) {                      // group complete: flush and move on
                 if (live && dirty) {
-                    pbase[(size_t)g * n_chains + chain] = s0;
-                    pbase[(size_t)(NG + g) * n_chains + chain] = s1;
+                    pbase[(size_t)g * n_chains + slot] = s0;
+                    pbase[(size_t)(NG + g) * n_chains + slot] = s1;
                 }
                 s0 = (T)0; s1 = (T)0; dirty = false;
                 ++g;
@@ -97,26 +130,26 @@ k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, c
     }
     if (live) {
         if (dirty && g < NG) {                         // group cut by the slab boundary
-            pbase[(size_t)g * n_chains + chain] = s0;
-            pbase[(size_t)(NG + g) * n_chains + chain] = s1;
+            pbase[(size_t)g * n_chains + slot] = s0;
+            pbase[(size_t)(NG + g) * n_chains + slot] = s1;
         }
-        pbase[(size_t)(2 * NG) * n_chains + chain] = ss;
+        pbase[(size_t)(2 * NG) * n_chains + slot] = ss;
     }
 }
 
 // warp per chain: combine slab partials (fixed order), add priors, chain rule to the free variables
 template <typename T>
 __global__ void k_hier_finalize(const T* __restrict__ part, const int* __restrict__ grp_off, int N, int NG,
-                                int n_splits, int rows_per_split, int n_chains, double mu_sd, double hc_beta,
+                                const int* cnt, const int* __restrict__ chain_of_slot, int grid_ctas,
+                                double mu_sd, double hc_beta,
                                 const T* qA, const T* qB, T* gA, T* gB, int ld, const B2ChainState* st, double* logp) {
-    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (chain >= n_chains) return;
-    int sel = 0;
-    if (st) {
-        if (st[chain].phase > B2_PHASE_HMC) return;
-        sel = st[chain].sel;
-    }
+    const HierGeom gm = hier_geom(cnt, grid_ctas, N);
+    if (slot >= gm.n_act) return;
+    const int chain = chain_of_slot[slot];
+    const int n_splits = gm.sp, rows_per_split = gm.rows_per_split, n_chains = gm.stride;
+    const int sel = st ? st[chain].sel : 0;
     const T* q = (sel ? qB : qA) + (size_t)chain * ld;
     T* gr = (sel ? gB : gA) + (size_t)chain * ld;
     const double mu_a = (double)q[0], ua = (double)q[1], mu_b = (double)q[2], ub = (double)q[3];
@@ -131,8 +164,8 @@ __global__ void k_hier_finalize(const T* __restrict__ part, const int* __restric
         if (hi > lo) {
             const int sp_lo = lo / rows_per_split, sp_hi = (hi - 1) / rows_per_split;
             for (int sp = sp_lo; sp <= sp_hi; ++sp) {
-                s0 += (double)part[sp * pstride + (size_t)g * n_chains + chain];
-                s1 += (double)part[sp * pstride + (size_t)(NG + g) * n_chains + chain];
+                s0 += (double)part[sp * pstride + (size_t)g * n_chains + slot];
+                s1 += (double)part[sp * pstride + (size_t)(NG + g) * n_chains + slot];
             }
         }
         s0 *= inv_e2; s1 *= inv_e2;
@@ -142,7 +175,7 @@ __global__ void k_hier_finalize(const T* __restrict__ part, const int* __restric
         gr[4 + g] = (T)(-a + sa * s0);
         gr[4 + NG + g] = (T)(-b + sb * s1);
     }
-    for (int sp = lane; sp < n_splits; sp += 32) acc[5] += (double)part[sp * pstride + (size_t)(2 * NG) * n_chains + chain];
+    for (int sp = lane; sp < n_splits; sp += 32) acc[5] += (double)part[sp * pstride + (size_t)(2 * NG) * n_chains + slot];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
         for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
@@ -167,26 +200,31 @@ int b2_hier_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
                    const B2ChainState* st, int n, double* logp, cudaStream_t stream) {
     const int N = e->md.N, NG = e->md.G;
     const int chain_tiles = (n + HT_CHAINS - 1) / HT_CHAINS;
-    // ~8 resident 128-thread blocks per SM and a grid that is a whole number of waves (148 SMs)
-    int splits = (8 * e->sm_count + chain_tiles / 2) / chain_tiles;
-    if (splits > (N + 255) / 256) splits = (N + 255) / 256;
-    if (splits < 1) splits = 1;
-    int rows_per_split = (N + splits - 1) / splits;
-    splits = (N + rows_per_split - 1) / rows_per_split;
-    const size_t need = (size_t)splits * (2 * NG + 1) * e->C * sizeof(T);
+    // fixed grid: ~8 resident 128-thread blocks per SM, a whole number of waves (148 SMs); the kernels divide
+    // it into (live chain tiles) x (observation slabs) themselves
+    int grid_ctas = 8 * e->sm_count;
+    if (grid_ctas < chain_tiles) grid_ctas = chain_tiles;
+    const size_t part_bytes = (size_t)grid_ctas * (2 * NG + 1) * HT_CHAINS * sizeof(T);
+    const size_t map_off = (part_bytes + 255) & ~(size_t)255;
+    const size_t need = map_off + ((size_t)e->C + 64) * sizeof(int);
     if (e->hier_ws_bytes < need) {
         if (e->hier_ws) cudaFree(e->hier_ws);
         e->hier_ws = nullptr; e->hier_ws_bytes = 0;
         B2_CUDA_OK(cudaMalloc(&e->hier_ws, need));
         e->hier_ws_bytes = need;
     }
-    dim3 grid(chain_tiles, splits);
-    k_hier_slab<T><<<grid, HT_CHAINS, 0, stream>>>(e->md.yf, e->md.floor_u8, e->md.grp_off, N, NG, qA, qB, ld, st, n,
-                                                   rows_per_split, (T*)e->hier_ws);
+    int* cnt = reinterpret_cast<int*>((char*)e->hier_ws + map_off);
+    int* chain_of_slot = cnt + 64;
+    B2_CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(int), stream));
+    k_hier_compact<<<(n + 255) / 256, 256, 0, stream>>>(st, n, cnt, chain_of_slot);
     B2_CUDA_OK(cudaGetLastError());
-    k_hier_finalize<T><<<(n + 3) / 4, 128, 0, stream>>>((const T*)e->hier_ws, e->md.grp_off, N, NG, splits, rows_per_split,
-                                                         n, e->md.hp[0], e->md.hp[1], qA, qB, gA, gB, ld, st, logp);
+    k_hier_slab<T><<<grid_ctas, HT_CHAINS, 0, stream>>>(e->md.yf, e->md.floor_u8, e->md.grp_off, N, NG, qA, qB, ld, st,
+                                                        cnt, chain_of_slot, (T*)e->hier_ws);
     B2_CUDA_OK(cudaGetLastError());
+    k_hier_finalize<T><<<(n + 3) / 4, 128, 0, stream>>>((const T*)e->hier_ws, e->md.grp_off, N, NG, cnt, chain_of_slot,
+                                                         grid_ctas, e->md.hp[0], e->md.hp[1], qA, qB, gA, gB, ld, st, logp);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 1;
     e->launches += 2;
     return 0;
 }
