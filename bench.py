@@ -258,7 +258,7 @@ def run_b200(args):
     barrier()
     if rank == 0 and not args.no_clocks:
         clocks.start()
-    eng.set_profiling(not args.no_profile)
+    eng.set_profiling(False)                 # per-launch events cost ~7 % of a lock-step step: separate pass P below
     launches0 = eng.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -270,8 +270,6 @@ def run_b200(args):
     wall_timed = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     clock_info = clocks.stop() if rank == 0 else None
-    like_ms, like_n = eng.profile()
-    adv_ms = eng.profile_advance()
     launches = eng.kernel_launches() - launches0
     reports = eng.reports()
     failed = sum(1 for r in reports if r.phase != _capi.PHASE_DONE)
@@ -313,6 +311,29 @@ def run_b200(args):
             dist.all_reduce(ess_t, op=dist.ReduceOp.SUM)                    # independent chain sets add
         ess_info = {"min_bulk_ess": float(ess_t.min().item()), "n_scalars": int(ess_t.numel()), "over": ess_note}
     del trace
+
+    # ---- pass P: the same job again with CUDA events around every likelihood / advance launch of the K timed
+    #      steps (kernel durations for the roofline; its own elapsed time is the denominator of the shares)
+    like_ms, like_n, adv_ms, prof_ms, leap_prof = 0.0, 0, 0.0, 0.0, 0
+    if not args.no_profile and rank == 0 and args.workload in ("c2", "c3"):     # the lock-step workloads
+        eng = new_engine()
+        ptrace = eng.alloc_trace(_capi.B2_NUTS, total)
+        for s in range(W):
+            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=s * ips)
+        torch.cuda.synchronize(dev)
+        eng.set_profiling(True)
+        pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pv0.record()
+        for s in range(K):
+            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=(W + s) * ips)
+        pv1.record()
+        torch.cuda.synchronize(dev)
+        prof_ms = pv0.elapsed_time(pv1)
+        like_ms, like_n = eng.profile()
+        adv_ms = eng.profile_advance()
+        leap_prof = int(ptrace["tree_size"][W * ips:].sum().item())
+        eng.close()
+        del ptrace
 
     # ---- pass B: end to end -- every step uploads its inputs from pinned host memory and reads
     #      its trace + stats back into pinned host memory (same seeds => same job)
@@ -358,11 +379,20 @@ def run_b200(args):
     if args.workload == "c2" and os.path.exists(tpath):        # one ncu --set full capture, per launch
         with open(tpath) as f:
             traffic = json.load(f).get("k_glm_tc_main", {}).get("dram_bytes_per_launch")
+    if args.workload == "c4":
+        # persistent kernel: one launch per step, so the per-unit figure of SURVEY 8d (70 KB per chain-grad if the
+        # state streamed through HBM) is set against the whole-step rate
+        ach = wl["bytes_per_chain_grad"] * value / max(world, 1) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "kernel": "k_persistent_block (whole NUTS transition loop, one launch per step)",
+                    "regime": "hot state (q, p, grad, p_sum, proposal, mass) is resident in shared memory, so the kernel is "
+                              "instruction-issue bound (ncu: issue slots 44 % busy, DRAM 27 GB/s), not HBM bound",
+                    "peak_source": peaks["source"]}
     if like_n > 0 and wl["bound"]:
         per_launch_s = like_ms / 1e3 / like_n
         # units one launch processes = chains still inside a trajectory (the launch skips finished chains and,
         # on the tensor-core path, compacts the live ones into dense tiles): counted, not assumed
-        units = leap_timed / like_n
+        units = leap_prof / like_n
         if wl["bound"] == "tensor":
             ach = wl["flops_per_chain_grad"] * units / per_launch_s / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
@@ -371,10 +401,16 @@ def run_b200(args):
             ach = wl["bytes_per_chain_grad"] * units / per_launch_s / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": ach / peaks["hbm_gbs"], "traffic": None}
+            if wl.get("flops_per_chain_grad"):
+                # once a tile of observations is shared by 128 chains the bound is FP32 issue, not HBM
+                fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # nominal: SMs x FP32 lanes x 2 x max SM clock
+                fl = wl["flops_per_chain_grad"] * units / per_launch_s / 1e12
+                roofline.update({"fp32_achieved_tflops": fl, "fp32_peak_tflops_nominal": fp32_peak, "fp32_frac": fl / fp32_peak})
         roofline.update({"kernel": "chain-batched likelihood (logp+dlogp, all chains)", "launches_timed": int(like_n),
                          "chain_grads_per_launch": units,
-                         "avg_launch_us": per_launch_s * 1e6, "kernel_share_of_step": like_ms / dev_ms,
-                         "advance_kernel_avg_us": adv_ms * 1e3 / like_n, "advance_share_of_step": adv_ms / dev_ms,
+                         "avg_launch_us": per_launch_s * 1e6, "kernel_share_of_step": like_ms / prof_ms,
+                         "advance_kernel_avg_us": adv_ms * 1e3 / like_n, "advance_share_of_step": adv_ms / prof_ms,
+                         "timed_in": "a separate identical pass with CUDA events around every launch (adds ~7 % to a step); value is measured without them",
                          "peak_source": peaks["source"]})
 
     cpu = None
