@@ -514,14 +514,15 @@ def run_c5(args):
         peaks = measured_peaks()
         per_step = t_timed / max(steps, 1)
         x_bytes = rows * k * 4.0
-        flops = 4.0 * rows * (k + 1) * chains
+        units = leap / max(steps, 1)                              # chain-gradients a lock-step step really processed
+        flops = 4.0 * rows * (k + 1) * units
         line = {"metric": "leapfrog_grad_evals_per_sec", "value": leap / t_timed, "unit": "grad-evals/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": t_timed * 1e3 / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
                 "config": {"workload": "logistic regression, observations sharded: %d rows x %d features per GPU, %d rows total"
                            % (rows, k, rows * world), "chains": chains, "iters_per_step": ips, "tune": tune, "draws": total - tune,
                            "collective": "all-reduce(sum) of [C, D+1] fp64 = %d bytes per leapfrog" % (chains * (k + 1) * 8)},
-                "lockstep_steps_timed": steps, "ms_per_leapfrog_all_chains": per_step * 1e3, "gpu_launches": launches,
+                "lockstep_steps_timed": steps, "chain_grads_per_step": units, "ms_per_leapfrog_all_chains": per_step * 1e3, "gpu_launches": launches,
                 "e2e": None,
                 "roofline": {"bound": "hbm", "achieved": x_bytes / per_step / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": x_bytes / per_step / 1e9 / peaks["hbm_gbs"], "traffic": None,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libb200nuts.so")
-SOURCES = ["b2_engine.cu", "b2_glm_simt.cu", "b2_hier.cu", "b2_glm_tc.cu"]
+SOURCES = ["b2_engine.cu", "b2_glm_simt.cu", "b2_hier.cu", "b2_glm_tc.cu", "b2_glm_tcw.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -29,6 +29,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd += os.environ.get("B2_NVCC_EXTRA", "").split()          # e.g. -DB2_TC_NOTRAP (debugging the tcgen05 pipelines)
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -228,7 +228,7 @@ static int launch_logp_group(b2_engine* e, const T* qA, const T* qB, T* gA, T* g
 static int pick_glm_path(const b2_engine* e, int requested) {
     if (e->md.family != B2_FAMILY_GLM_LOGIT) return B2_GLM_GROUP;
     if (requested == B2_GLM_AUTO) {
-        if (e->dtype == B2_F32 && b2_glm_tc_supported(e)) return B2_GLM_TCGEN05;
+        if (e->dtype == B2_F32 && (b2_glm_tc_supported(e) || b2_glm_tcw_supported(e))) return B2_GLM_TCGEN05;
         return ((size_t)e->md.N * e->C >= (size_t)1 << 16) ? B2_GLM_SIMT : B2_GLM_GROUP;
     }
     return requested;
@@ -245,6 +245,7 @@ int launch_likelihood<float>(b2_engine* e, const float* qA, const float* qB, flo
     if (e->md.family == B2_FAMILY_GLM_LOGIT) {
         const int path = pick_glm_path(e, glm_path);
         if (path == B2_GLM_TCGEN05) {
+            if (b2_glm_tcw_supported(e)) return b2_glm_tcw_launch(e, qA, qB, gA, gB, ld, st, n, logp, s);
             if (!b2_glm_tc_supported(e)) { b2_set_error("tcgen05 GLM path does not support this shape"); return -6; }
             return b2_glm_tc_launch(e, qA, qB, gA, gB, ld, st, n, logp, s);
         }
@@ -322,6 +323,7 @@ extern "C" int b2_engine_destroy(b2_engine* e) {
     cudaSetDevice(e->device);
     cudaFree(e->vec); cudaFree(e->wv_mean); cudaFree(e->wv_m2); cudaFree(e->st); cudaFree(e->lv); cudaFree(e->logp_eval);
     b2_glm_tc_release(e);
+    b2_glm_tcw_release(e);
     cudaFree(e->glm_scratch); cudaFree(e->d_active); cudaFree(e->glm_ws); cudaFree(e->hier_ws);
     cudaFreeHost(e->h_active);
     if (e->ev[0]) for (int i = 0; i < 96; ++i) cudaEventDestroy(e->ev[i]);
@@ -460,7 +462,7 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         const int batch = 32;
         // GLM on the tensor-core path: {tcgen05 likelihood, fused finalize+advance+repack} per step
         const bool fused_tc = sizeof(T) == 4 && !blk && e->md.family == B2_FAMILY_GLM_LOGIT &&
-                              pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05;
+                              pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05 && !b2_glm_tcw_supported(e);
         if (fused_tc && !b2_glm_tc_supported(e)) { b2_set_error("tcgen05 GLM path does not support this shape"); return -6; }
         if (e->iter_done > 0) {                       // re-activate chains that finished the previous call
             if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 1);

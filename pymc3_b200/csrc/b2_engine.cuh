@@ -22,6 +22,7 @@ struct b2_engine {
     void* glm_ws;              // workspace of the chain-batched GLM kernels (b2_glm_*.cu)
     size_t glm_ws_bytes;
     void* glm_tc;              // state of the tcgen05 GLM path (b2_glm_tc.cu), or null
+    void* glm_tcw;             // state of the wide (128 <= K <= 256) tcgen05 GLM path (b2_glm_tcw.cu), or null
     void* hier_ws;             // workspace of the chain-batched hierarchical kernel
     size_t hier_ws_bytes;
     int iter_done;             // iterations completed by every chain so far
@@ -58,6 +59,11 @@ int b2_glm_simt_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int
 int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
                      const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);
 bool b2_glm_tc_supported(const b2_engine* e);
+// wide variant (128 <= K <= 256 features, b2_glm_tcw.cu): likelihood launch only, no fused companion kernel
+bool b2_glm_tcw_supported(const b2_engine* e);
+void b2_glm_tcw_release(b2_engine* e);
+int b2_glm_tcw_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
+                      const B2ChainState* st, int n, double* logp, cudaStream_t stream);
 void b2_glm_tc_release(b2_engine* e);
 // fused lock-step pieces of the tensor-core path: split/swizzle the pending positions, run the
 // likelihood, then {reduce slab partials, advance the chain state machine, re-split} in one kernel

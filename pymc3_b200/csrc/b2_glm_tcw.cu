@@ -1,0 +1,455 @@
+// Wide variant of the tensor-core Bernoulli-logit GLM likelihood: 128 <= K <= 256 feature columns
+// (config C5: K = 256 features + intercept; reference: pymc3/glm/linear.py:49-101, glm/families.py:115-119,
+// evaluated by ValueGradFunction.__call__, model.py:645-666).  Same algorithm as b2_glm_tc.cu
+//
+//   GEMM1  S[128 chains, 32 obs]    = Q . Xtile^T        (K up to 256: 16 K steps x 3 bf16 split passes)
+//   epi    R = y - sigmoid(S + q0),  logp += ...          (the intercept q0 is added here, not in the GEMM)
+//   GEMM2  G[128 chains, 128 feat] += R . Xtile[:, half]  (MN-major read of the SAME shared-memory tile)
+//
+// with the tensor-memory budget re-cut for twice the features.  512 TMEM columns hold S 2x32, R 2x32
+// (bf16 hi | lo), Q 256 (bf16 hi | lo of 256 features) and ONE 128-feature half of G, so a CTA owns
+// (chain tile, observation slab, feature half): the two CTAs of a pair walk the same X tiles (second reader
+// hits L2), both run GEMM1 and the epilogue, each accumulates its half of the gradient.  Tensor work per
+// 32-observation tile and CTA: GEMM1 768 + GEMM2 384 cycles against 768 + 768 for an (impossible) unsplit
+// CTA, i.e. 2/3 efficiency from the duplicated GEMM1 -- and 25x the SIMT kernel it replaces.
+// A tile is 32 observations so that a pipeline stage stays one 32 KB bulk copy (+128 B of y).
+// The intercept never enters the GEMMs (K = 256 would become 257): eta = S + q0 in the epilogue, and its
+// gradient is the row sum of R, accumulated next to logp.  Zero-padded rows carry y = -1 and are masked.
+#include <cstring>
+#include <cstdlib>
+#include "b2_engine.cuh"
+#include "b2_tc_ptx.cuh"
+
+#define TW_CHAINS 128
+#define TW_OBS 32
+#define TW_KP 256
+#define TW_STAGES 6
+#define TW_XPART_BYTES (TW_OBS * TW_KP * 2)             // 16384: one of {hi, lo}, four 64-column atoms of 32 rows
+#define TW_Y_BYTES (TW_OBS * 4)                         // 128
+#define TW_STAGE_DATA (2 * TW_XPART_BYTES + TW_Y_BYTES) // 32896 in global memory: Xhi | Xlo | y
+#define TW_STAGE_BYTES (2 * TW_XPART_BYTES)
+#define TW_SMEM_BYTES (1024 + TW_STAGES * (TW_STAGE_BYTES + TW_Y_BYTES) + 512)
+#define TW_EPI_GROUPS 4                                 // epilogue warpgroups; group g takes tiles t = g (mod 4)
+#define TW_EPI_WARPS (4 * TW_EPI_GROUPS)
+#define TW_THREADS (128 + 32 * TW_EPI_WARPS)
+#define TW_TMEM_COLS 512
+#define TW_COL_S 0                                      // S[b] at 32 b
+#define TW_COL_P 64                                     // R[b] at 64 + 32 b: hi 16 cols | lo 16 cols
+#define TW_COL_G 128                                    // 128 columns (this CTA's feature half)
+#define TW_COL_Q 256                                    // hi 128 cols | lo 128 cols
+
+struct TwWorkspace {
+    unsigned char* xt;       // [n_tiles][TW_STAGE_DATA]
+    float* gpart;            // [slab][slot][TW_KP]
+    double* lpart;           // [slab][TW_EPI_GROUPS][slot]
+    double* rpart;           // [slab][TW_EPI_GROUPS][slot]   row sums of R (intercept gradient)
+    int n_tiles, chain_tiles, grid_ctas;
+    int* err;
+    const float* qA; const float* qB; int ld; const B2ChainState* st; int n_chains; int K;
+    int* counter;            // live chains of this launch
+    int* chain_of_slot;
+};
+
+struct TwGeom { int n_act, nt, sp, tps, stride; };
+__device__ __forceinline__ TwGeom tw_geom(const TwWorkspace& ws) {
+    TwGeom g;
+    g.n_act = *ws.counter;
+    g.nt = (g.n_act + TW_CHAINS - 1) / TW_CHAINS;
+    g.sp = g.nt > 0 ? (ws.grid_ctas / 2) / g.nt : 1;
+    if (g.sp > ws.n_tiles) g.sp = ws.n_tiles;
+    if (g.sp < 1) g.sp = 1;
+    g.tps = (ws.n_tiles + g.sp - 1) / g.sp;
+    g.sp = (ws.n_tiles + g.tps - 1) / g.tps;
+    g.stride = g.nt * TW_CHAINS;
+    return g;
+}
+
+__global__ void k_glm_tcw_prep_x(const float* __restrict__ X, const float* __restrict__ y, int N, int K,
+                                 unsigned char* __restrict__ xt) {
+    const int tile = blockIdx.x;
+    unsigned char* blob = xt + (size_t)tile * TW_STAGE_DATA;
+    for (int idx = threadIdx.x; idx < TW_OBS * TW_KP; idx += blockDim.x) {
+        const int r = idx / TW_KP, c = idx - r * TW_KP;
+        const int row = tile * TW_OBS + r;
+        const float v = (row < N && c < K) ? X[(size_t)row * K + c] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int off = (c >> 6) * (TW_OBS * 128) + tc_swz(r, c & 63);
+        *reinterpret_cast<__nv_bfloat16*>(blob + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(blob + TW_XPART_BYTES + off) = lo;
+    }
+    for (int r = threadIdx.x; r < TW_OBS; r += blockDim.x) {
+        const int row = tile * TW_OBS + r;
+        reinterpret_cast<float*>(blob + 2 * TW_XPART_BYTES)[r] = row < N ? y[row] : -1.f;   // -1: padding row
+    }
+}
+
+__global__ void k_glm_tcw_compact(const B2ChainState* st, int n_chains, int* cnt, int* chain_of_slot) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    if (!st) { chain_of_slot[c] = c; if (c == 0) *cnt = n_chains; return; }
+    if (!b2_needs_grad(st[c].phase)) return;
+    chain_of_slot[atomicAdd(cnt, 1)] = c;
+}
+
+__global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* x_s = smem;
+    unsigned char* y_s = x_s + TW_STAGES * TW_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(y_s + TW_STAGES * TW_Y_BYTES);
+    uint64_t* q_full = bars;                       // 1
+    uint64_t* x_full = bars + 1;                   // TW_STAGES
+    uint64_t* x_empty = x_full + TW_STAGES;        // TW_STAGES
+    // S and R are double-buffered (b = t & 1) but their barriers are per tile-mod-4 (= per epilogue group): a
+    // barrier must only ever be waited on by one agent walking its phases in order -- a group that starts on a
+    // fresh barrier with parity 1 falls straight through (the phase "before" phase 0 counts as complete).
+    uint64_t* s_full = x_empty + TW_STAGES;        // 4
+    uint64_t* s_empty = s_full + 4;                // 4
+    uint64_t* p_full = s_empty + 4;                // 4
+    uint64_t* p_empty = p_full + 4;                // 4
+    uint64_t* g_full = p_empty + 4;                // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TwGeom gm = tw_geom(ws);
+    const int pair = blockIdx.x >> 1, half = blockIdx.x & 1;
+    if (gm.nt == 0 || pair >= gm.nt * gm.sp) return;
+    const int ctile = pair / gm.sp, split = pair % gm.sp;
+    const int t_begin = split * gm.tps;
+    const int t_end = min(ws.n_tiles, t_begin + gm.tps);
+    const int T = t_end - t_begin;                 // >= 1
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, TW_EPI_WARPS);
+        for (int i = 0; i < TW_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 4); mbar_init(p_full + i, 4); mbar_init(p_empty + i, 1); }
+        mbar_init(g_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TW_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: the X tile ring (one 32 KB + one 128 B bulk copy per stage)
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                const int s = t % TW_STAGES;
+                if (t >= TW_STAGES) mbar_wait(x_empty + s, ((t / TW_STAGES) - 1) & 1, ws.err, 1);
+                const unsigned char* src = ws.xt + (size_t)(t_begin + t) * TW_STAGE_DATA;
+                mbar_expect_tx(x_full + s, TW_STAGE_DATA);
+                bulk_g2s(x_s + s * TW_STAGE_BYTES, src, TW_STAGE_BYTES, x_full + s);
+                bulk_g2s(y_s + s * TW_Y_BYTES, src + TW_STAGE_BYTES, TW_Y_BYTES, x_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== GEMM1 issuer (whole warp runs the uniform loop, one elected lane issues)
+        mbar_wait(q_full, 0, ws.err, 2);
+        tc_fence_after();
+        const int ks = (ws.K + 15) >> 4;                           // <= 16
+        const uint32_t idesc_g1 = TC_IDESC_BASE | ((TW_OBS >> 3) << 17) | ((TW_CHAINS >> 4) << 24);   // N = 32, K-major B
+        for (int t = 0; t < T; ++t) {
+            const int s = t % TW_STAGES, b = t & 1;
+            mbar_wait(x_full + s, (t / TW_STAGES) & 1, ws.err, 3);
+            if (t >= 2) mbar_wait(s_empty + ((t - 2) & 3), ((t - 2) >> 2) & 1, ws.err, 4);   // S[b] of tile t-2 is in registers
+            tc_fence_after();
+            const uint32_t x_addr = smem_u32(x_s + s * TW_STAGE_BYTES);
+            const uint32_t d = tmem + TW_COL_S + 32 * b;
+            if (elect_one()) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {              // Qhi.Xhi, Qlo.Xhi, Qhi.Xlo
+                    const uint32_t qa = tmem + TW_COL_Q + (pass == 1 ? 128 : 0);
+                    const uint32_t xa = x_addr + (pass == 2 ? TW_XPART_BYTES : 0);
+#pragma unroll
+                    for (int j = 0; j < TW_KP / 16; ++j) {
+                        if (j >= ks) break;
+                        const uint64_t bd = make_desc(xa + (j >> 2) * (TW_OBS * 128) + (j & 3) * 32, 16, 1024);
+                        mma_ts(d, qa + j * 8, bd, idesc_g1, acc);
+                        acc = 1;
+                    }
+                }
+                tc_commit(s_full + (t & 3));
+            }
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ===== GEMM2 issuer: this CTA's feature half, N = its live features rounded up to 16
+        int kh = ws.K - 128 * half;
+        kh = kh > 128 ? 128 : (kh < 1 ? 1 : kh);                 // K = 128: the second half is all padding, N = 16 of zeros
+        const uint32_t n2 = (uint32_t)((kh + 15) & ~15);
+        const uint32_t idesc_g2 = TC_IDESC_BASE | (1u << 16) | ((n2 >> 3) << 17) | ((TW_CHAINS >> 4) << 24);
+        for (int u = 0; u < T; ++u) {
+            const int s = u % TW_STAGES, b = u & 1;
+            mbar_wait(p_full + (u & 3), (u >> 2) & 1, ws.err, 5);
+            tc_fence_after();
+            const uint32_t x_addr = smem_u32(x_s + s * TW_STAGE_BYTES) + half * 2 * (TW_OBS * 128);
+            const uint32_t p_base = tmem + TW_COL_P + 32 * b;
+            const uint32_t d = tmem + TW_COL_G;
+            if (elect_one()) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {              // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
+                    const uint32_t pa = p_base + (pass == 1 ? 16 : 0);
+                    const uint32_t xa = x_addr + (pass == 2 ? TW_XPART_BYTES : 0);
+#pragma unroll
+                    for (int j = 0; j < TW_OBS / 16; ++j) {
+                        // MN-major B: 64-feature atoms LBO = 4096 B apart, 8-row groups SBO = 1024 B apart
+                        const uint64_t bd = make_desc(xa + j * 2048, TW_OBS * 128, 1024);
+                        mma_ts(d, pa + j * 8, bd, idesc_g2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(x_empty + s);
+                tc_commit(p_empty + (u & 3));
+                if (u == T - 1) tc_commit(g_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warpgroups: thread == chain row; group cg owns every 4th tile (32 observation columns)
+        const int wq = warp & 3;                                     // TMEM lane quarter this warp may touch
+        const int cg = (warp - 4) >> 2;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const int slot = ctile * TW_CHAINS + row;
+        const bool live = slot < gm.n_act;
+        float q0 = 0.f;
+        {   // Q (A operand of GEMM1): this chain's row, features 64cg..64cg+63, bf16 hi/lo split
+            const int chain = live ? ws.chain_of_slot[slot] : 0;
+            int sel = 0;
+            if (live && ws.st) sel = ws.st[chain].sel;
+            const float* q = (sel ? ws.qB : ws.qA) + (size_t)chain * ws.ld;
+            if (live) q0 = q[0];
+#pragma unroll
+            for (int rnd = 0; rnd < 2; ++rnd) {
+                uint32_t qh[16], ql[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = 64 * cg + 32 * rnd + 2 * i;
+                    const float a = (live && k < ws.K) ? q[1 + k] : 0.f;
+                    const float b2 = (live && k + 1 < ws.K) ? q[2 + k] : 0.f;
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b2);
+                    const float2 back = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - back.x, b2 - back.y);
+                    qh[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    ql[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                TC_ST16(tmem + lane_addr + TW_COL_Q + 32 * cg + 16 * rnd, qh);
+                TC_ST16(tmem + lane_addr + TW_COL_Q + 128 + 32 * cg + 16 * rnd, ql);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_full);
+        }
+        float lp_sum = 0.f, lp_comp = 0.f, r_sum = 0.f, r_comp = 0.f;   // Kahan: no fp64 in the tile loop
+        for (int t = cg; t < T; t += TW_EPI_GROUPS) {
+            const int s = t % TW_STAGES, b = t & 1;
+            const float4* ys4 = reinterpret_cast<const float4*>(y_s + s * TW_Y_BYTES);
+            mbar_wait(s_full + cg, (t >> 2) & 1, ws.err, 6);
+            // y values of this stage: the phase is already complete (GEMM1 of this tile consumed the stage) and the
+            // next one cannot complete before this tile's R is handed to GEMM2, so the parity test is unambiguous
+            mbar_wait(x_full + s, (t / TW_STAGES) & 1, ws.err, 9);
+            tc_fence_after();
+            uint32_t v[2][16];
+            TC_LD16(tmem + lane_addr + TW_COL_S + 32 * b, v[0]);
+            TC_LD16(tmem + lane_addr + TW_COL_S + 32 * b + 16, v[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + cg);                // S(t) is in registers
+            uint32_t hi[2][8], lo[2][8];
+            float lsum = 0.f, rsum = 0.f;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float yv[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 y4 = ys4[4 * hh + i];
+                    yv[4 * i] = y4.x; yv[4 * i + 1] = y4.y; yv[4 * i + 2] = y4.z; yv[4 * i + 3] = y4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float r2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float eta = __uint_as_float(v[hh][2 * i + h]) + q0;
+                        const float yy = yv[2 * i + h];
+                        const bool valid = yy >= 0.f;
+                        const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
+                        const float w1 = 1.f + e;
+                        const float inv = tc_rcp(w1);
+                        const float sig = eta >= 0.f ? inv : e * inv;
+                        if (half == 0) {                             // logp is counted by one CTA of the pair
+                            const float term = fmaf(yy, eta, -fmaf(0.6931471805599453f, tc_lg2(w1), fmaxf(eta, 0.f)));
+                            lsum += valid ? term : 0.f;
+                        }
+                        r2[h] = valid ? yy - sig : 0.f;
+                        rsum += r2[h];
+                    }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
+                    const float2 back = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
+                    hi[hh][i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[hh][i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+            }
+            if (t >= 2) mbar_wait(p_empty + ((t - 2) & 3), ((t - 2) >> 2) & 1, ws.err, 7);   // GEMM2 of tile t-2 has read R[b]
+            tc_fence_after();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                TC_ST8(tmem + lane_addr + TW_COL_P + 32 * b + 8 * hh, hi[hh]);
+                TC_ST8(tmem + lane_addr + TW_COL_P + 32 * b + 16 + 8 * hh, lo[hh]);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full + cg);
+            float ky = lsum - lp_comp, kt = lp_sum + ky;
+            lp_comp = (kt - lp_sum) - ky; lp_sum = kt;
+            ky = rsum - r_comp; kt = r_sum + ky;
+            r_comp = (kt - r_sum) - ky; r_sum = kt;
+        }
+        // the slab's gradient tile: G[chain row][this half's 128 features] -> global partials
+        mbar_wait(g_full, 0, ws.err, 8);
+        tc_fence_after();
+        float* gout = ws.gpart + ((size_t)split * gm.stride + slot) * TW_KP + 128 * half + 32 * cg;
+        {
+            uint32_t g32[32];
+            TC_LD32(tmem + lane_addr + TW_COL_G + 32 * cg, g32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(gout)[i] =
+                    make_float4(__uint_as_float(g32[4 * i]), __uint_as_float(g32[4 * i + 1]),
+                                __uint_as_float(g32[4 * i + 2]), __uint_as_float(g32[4 * i + 3]));
+        }
+        if (half == 0) {
+            const size_t o = ((size_t)split * TW_EPI_GROUPS + cg) * gm.stride + slot;
+            ws.lpart[o] = (double)lp_sum - (double)lp_comp;
+            ws.rpart[o] = (double)r_sum - (double)r_comp;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TW_TMEM_COLS) : "memory");
+    }
+}
+
+// one warp per live chain: fixed-order reduction over slabs, prior, intercept gradient
+__global__ void k_glm_tcw_finalize(TwWorkspace ws, double prior_tau, float* gA, float* gB, double* logp) {
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const TwGeom gm = tw_geom(ws);
+    if (slot >= gm.n_act) return;
+    const int chain = ws.chain_of_slot[slot];
+    const int sel = ws.st ? ws.st[chain].sel : 0;
+    const float* q = (sel ? ws.qB : ws.qA) + (size_t)chain * ws.ld;
+    float* g = (sel ? gB : gA) + (size_t)chain * ws.ld;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float4* gp = reinterpret_cast<const float4*>(ws.gpart + (size_t)slot * TW_KP) + 2 * lane;
+    const size_t stride4 = (size_t)gm.stride * TW_KP / 4;
+    for (int sp = 0; sp < gm.sp; ++sp) {
+        const float4 a = __ldcg(gp + (size_t)sp * stride4), b = __ldcg(gp + (size_t)sp * stride4 + 1);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    double lp = 0.0, rs = 0.0, prior = 0.0;
+    const int n_lp = gm.sp * TW_EPI_GROUPS;
+    for (int i = lane; i < n_lp; i += 32) {
+        lp += ws.lpart[(size_t)i * gm.stride + slot];
+        rs += ws.rpart[(size_t)i * gm.stride + slot];
+    }
+    const double prior_const = 0.5 * (log(prior_tau) - B2_LOG_2PI);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = 8 * lane + j;
+        if (k < ws.K) {
+            const double b = (double)q[1 + k];
+            g[1 + k] = (float)((double)acc[j] - prior_tau * b);
+            prior += -0.5 * prior_tau * b * b + prior_const;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lp += __shfl_xor_sync(0xffffffffu, lp, o);
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        prior += __shfl_xor_sync(0xffffffffu, prior, o);
+    }
+    if (lane == 0) {
+        g[0] = (float)rs;                                   // intercept: Flat prior (glm/linear.py:50)
+        logp[chain] = lp + prior;
+    }
+}
+
+// ---------------------------------------------------------------------------------- host
+struct TwHostState { TwWorkspace ws; };
+
+bool b2_glm_tcw_supported(const b2_engine* e) {
+    return e->md.family == B2_FAMILY_GLM_LOGIT && e->dtype == B2_F32 && e->md.G >= 128 && e->md.G <= TW_KP && e->md.N >= 1;
+}
+
+static int tw_setup(b2_engine* e, cudaStream_t stream) {
+    TwHostState* hs = new TwHostState();
+    memset(hs, 0, sizeof(*hs));
+    TwWorkspace& w = hs->ws;
+    const int N = e->md.N;
+    w.n_tiles = (N + TW_OBS - 1) / TW_OBS;
+    w.chain_tiles = (e->C + TW_CHAINS - 1) / TW_CHAINS;
+    w.grid_ctas = 2 * (e->sm_count / 2);                     // CTA pairs (feature halves), one CTA per SM
+    if (w.grid_ctas < 2 * w.chain_tiles) w.grid_ctas = 2 * w.chain_tiles;
+    const size_t slabs = (size_t)w.grid_ctas / 2 + w.chain_tiles;
+    B2_CUDA_OK(cudaMalloc(&w.counter, 64 * sizeof(int)));
+    B2_CUDA_OK(cudaMalloc(&w.chain_of_slot, (size_t)w.chain_tiles * TW_CHAINS * sizeof(int)));
+    B2_CUDA_OK(cudaMalloc(&w.xt, (size_t)w.n_tiles * TW_STAGE_DATA));
+    B2_CUDA_OK(cudaMalloc(&w.gpart, slabs * TW_CHAINS * TW_KP * sizeof(float)));
+    B2_CUDA_OK(cudaMalloc(&w.lpart, slabs * TW_EPI_GROUPS * TW_CHAINS * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&w.rpart, slabs * TW_EPI_GROUPS * TW_CHAINS * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc(&w.err, TC_ERR_INTS * sizeof(int)));
+    B2_CUDA_OK(cudaMemsetAsync(w.err, 0, TC_ERR_INTS * sizeof(int), stream));
+    k_glm_tcw_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt);
+    B2_CUDA_OK(cudaGetLastError());
+    B2_CUDA_OK(cudaFuncSetAttribute(k_glm_tcw_main, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES));
+    e->launches += 1;
+    e->glm_tcw = hs;
+    return 0;
+}
+
+void b2_glm_tcw_release(b2_engine* e) {
+    if (!e->glm_tcw) return;
+    TwHostState* hs = (TwHostState*)e->glm_tcw;
+    cudaFree(hs->ws.xt); cudaFree(hs->ws.counter); cudaFree(hs->ws.chain_of_slot); cudaFree(hs->ws.gpart);
+    cudaFree(hs->ws.lpart); cudaFree(hs->ws.rpart); cudaFree(hs->ws.err);
+    delete hs;
+    e->glm_tcw = nullptr;
+}
+
+int b2_glm_tcw_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
+                      const B2ChainState* st, int n, double* logp, cudaStream_t stream) {
+    if (!e->glm_tcw) { int rc = tw_setup(e, stream); if (rc) return rc; }
+    TwWorkspace& w = ((TwHostState*)e->glm_tcw)->ws;
+    w.qA = qA; w.qB = qB; w.ld = ld; w.st = st; w.n_chains = n; w.K = e->md.G;
+    B2_CUDA_OK(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
+    k_glm_tcw_compact<<<(n + 255) / 256, 256, 0, stream>>>(st, n, w.counter, w.chain_of_slot);
+    B2_CUDA_OK(cudaGetLastError());
+    k_glm_tcw_main<<<w.grid_ctas, TW_THREADS, TW_SMEM_BYTES, stream>>>(w);
+    B2_CUDA_OK(cudaGetLastError());
+    k_glm_tcw_finalize<<<(n + 3) / 4, 128, 0, stream>>>(w, e->md.hp[0], gA, gB, logp);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 3;
+    return 0;
+}
+
+// debugging aid (B2_TC_NOTRAP builds): first stuck mbarrier wait = tag + 100 * warp + 10000 * CTA, 0 if none
+extern "C" int b2_debug_tcw_err(b2_engine* e, int* host_out) {
+    if (!e || !e->glm_tcw) return -1;
+    B2_CUDA_OK(cudaDeviceSynchronize());
+    B2_CUDA_OK(cudaMemcpy(host_out, ((TwHostState*)e->glm_tcw)->ws.err, TC_ERR_INTS * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}

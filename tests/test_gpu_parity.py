@@ -58,6 +58,43 @@ def test_glm_tcgen05_path_matches_oracle():
         eng.close()
 
 
+def test_glm_wide_tcgen05_path_matches_oracle():
+    """128 <= K <= 256 features (config C5's D = 256): CTA pairs own the two feature halves, the intercept is
+    added in the epilogue; ragged N (masked padding rows), partial second half, partial chain tile"""
+    from oracle import densities as od
+    from pymc3_b200 import model as pm
+    for n, k, chains in [(3000 + 17, 256, 140), (2048, 200, 40), (500, 128, 3), (40000, 256, 256)]:
+        X, y = models_util.glm_data(n, k, seed=8)
+        model, oracle = pm.LogisticGLM(X, y), od.LogisticGLM(X, y)
+        rng = np.random.default_rng(6)
+        q = (rng.normal(size=(chains, oracle.ndim)) * 0.3).astype("f4")
+        eng = model.engine(chains, dtype="float32")
+        logp, grad = eng.logp_dlogp(q, glm_path=_capi.B2_GLM_TCGEN05)
+        logp, grad = logp.cpu().numpy(), grad.cpu().numpy().astype("f8")
+        for i in range(0, chains, max(1, chains // 12)):
+            l0, g0 = oracle(q[i].astype("f8"))
+            assert abs(logp[i] - l0) <= 1e-4 * abs(l0), (n, k, i, logp[i], l0)
+            assert _rel(grad[i], g0) <= 1e-4, (n, k, i, _rel(grad[i], g0))
+        eng.close()
+
+
+def test_glm_wide_tcgen05_lockstep_agrees_with_simt_lockstep():
+    """K = 160: the auto path is the wide tensor-core likelihood + plain advance kernel; same chains on the SIMT
+    likelihood agree for the first transitions (fp32 round-off diverges chaotically afterwards)"""
+    from pymc3_b200 import model as pm
+    X, y = models_util.glm_data(6000, 160, seed=11)
+    model = pm.LogisticGLM(X, y)
+    C, D = 20, 161
+    q0 = np.random.default_rng(12).uniform(-1, 1, size=(C, D)) * 0.1
+    seeds = np.arange(C) + 500
+    a = _run_engine(model, q0, seeds, 12, 12, _capi.B2_NUTS, "float32", _capi.B2_EXEC_LOCKSTEP, glm_path=_capi.B2_GLM_TCGEN05)
+    b = _run_engine(model, q0, seeds, 12, 12, _capi.B2_NUTS, "float32", _capi.B2_EXEC_LOCKSTEP, glm_path=_capi.B2_GLM_SIMT)
+    assert (a["depth"][:6] == b["depth"][:6]).mean() > 0.95
+    assert np.abs(a["q"][:4] - b["q"][:4]).max() < 5e-3
+    assert all(r.phase == _capi.PHASE_DONE for r in a["reports"])
+    assert np.isfinite(a["energy"]).all()
+
+
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-6), ("float32", 1e-4)])
 @pytest.mark.parametrize("path", [_capi.B2_GLM_GROUP, _capi.B2_GLM_SIMT])
 def test_glm_chain_batched_paths(dtype, tol, path):
