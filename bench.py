@@ -250,8 +250,13 @@ def run_b200(args):
     trace = eng.alloc_trace(_capi.B2_NUTS, total)          # the whole job's device trace, allocated up front
     barrier()
     tw0 = time.perf_counter()
+    ahead = args.run_ahead                 # lock-step runs: fast chains go on into the next step's rows (no-op otherwise)
+
+    def grads(e):
+        return sum(r.n_grad for r in e.reports())
+
     for s in range(W):
-        eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=s * ips)
+        eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=s * ips, run_ahead=ahead)
     torch.cuda.synchronize(dev)
     wall_warm = time.perf_counter() - tw0
     clocks = ClockSampler(local_rank)
@@ -260,11 +265,12 @@ def run_b200(args):
         clocks.start()
     eng.set_profiling(False)                 # per-launch events cost ~7 % of a lock-step step: separate pass P below
     launches0 = eng.kernel_launches()
+    grads0 = grads(eng)                      # leapfrogs are counted when they are executed (engine counters)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
     for s in range(K):
-        eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=(W + s) * ips)
+        eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=(W + s) * ips, run_ahead=ahead)
     ev1.record()
     barrier()
     wall_timed = time.perf_counter() - t0
@@ -272,11 +278,11 @@ def run_b200(args):
     clock_info = clocks.stop() if rank == 0 else None
     launches = eng.kernel_launches() - launches0
     reports = eng.reports()
+    leap_timed = sum(r.n_grad for r in reports) - grads0
     failed = sum(1 for r in reports if r.phase != _capi.PHASE_DONE)
     eng.close()
 
     tree = trace["tree_size"]                                           # [total, C]
-    leap_timed = int(tree[W * ips:].sum().item())
     leap_all = int(tree.sum().item())
     t_vec = torch.tensor([dev_ms / 1e3, wall_timed, wall_warm], dtype=torch.float64, device=dev)
     cnt = torch.tensor([leap_timed, leap_all, launches, failed], dtype=torch.float64, device=dev)
@@ -319,19 +325,20 @@ def run_b200(args):
         eng = new_engine()
         ptrace = eng.alloc_trace(_capi.B2_NUTS, total)
         for s in range(W):
-            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=s * ips)
+            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=s * ips, run_ahead=ahead)
         torch.cuda.synchronize(dev)
         eng.set_profiling(True)
+        pg0 = grads(eng)
         pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pv0.record()
         for s in range(K):
-            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=(W + s) * ips)
+            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=(W + s) * ips, run_ahead=ahead)
         pv1.record()
         torch.cuda.synchronize(dev)
         prof_ms = pv0.elapsed_time(pv1)
         like_ms, like_n = eng.profile()
         adv_ms = eng.profile_advance()
-        leap_prof = int(ptrace["tree_size"][W * ips:].sum().item())
+        leap_prof = grads(eng) - pg0
         eng.close()
         del ptrace
 
@@ -341,23 +348,25 @@ def run_b200(args):
     host_in = [t.cpu().pin_memory() for t in eng._keep]
     h2d = sum(t.numel() * t.element_size() for t in host_in)
     pinned, d2h = {}, 0
+    etrace = eng.alloc_trace(_capi.B2_NUTS, total)
     for s in range(W):
-        eng.run(_capi.B2_NUTS, ips, tune, opts)
+        eng.run(_capi.B2_NUTS, ips, tune, opts, out=etrace, row0=s * ips, run_ahead=ahead)
     barrier()
+    eg0 = grads(eng)
     e0 = time.perf_counter()
-    leap_e2e = 0
     for s in range(K):
         for src, dst in zip(host_in, eng._keep):
             dst.copy_(src, non_blocking=True)
-        out = eng.run(_capi.B2_NUTS, ips, tune, opts)
-        for name, t in out.items():
+        out = eng.run(_capi.B2_NUTS, ips, tune, opts, out=etrace, row0=(W + s) * ips, run_ahead=ahead)
+        for name, t in out.items():                    # this step's rows are complete for every chain
             if name not in pinned:
                 pinned[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             pinned[name].copy_(t, non_blocking=True)
         torch.cuda.synchronize(dev)
-        leap_e2e += int(pinned["tree_size"].sum().item())
     barrier()
     e2e_s = time.perf_counter() - e0
+    leap_e2e = grads(eng) - eg0
+    del etrace
     d2h = sum(t.numel() * t.element_size() for t in pinned.values())
     eng.close()
     e_vec = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -428,7 +437,9 @@ def run_b200(args):
         "config": {"workload": wl["label"], "chains_per_gpu": chains, "chains_total": chains * world,
                    "iters_per_step": ips, "tune": tune, "draws": total - tune, "sampler": "NUTS target_accept=0.8",
                    "l2": L2_NOTES.get(args.workload, "inputs change every launch"),
-                   "grad_evals_counted": "sum of tree_size (leapfrogs) in the timed steps"},
+                   "grad_evals_counted": "engine leapfrog counters read before and after the timed steps",
+                   "step_boundaries": ("lock-step chains that finish a step early run ahead into the next step's rows; a step "
+                                       "ends when every chain has done its transitions" if ahead else "all chains stop at every step boundary")},
         # whole sampling job incl. tuning (mirrors benchmarks/benchmarks/benchmarks.py:163-169)
         "min_bulk_ess_per_sec": (ess_info["min_bulk_ess"] / (t_timed + float(t_vec[2].item()))
                                  if ess_info else None),
@@ -567,6 +578,9 @@ def main():
     ap.add_argument("--n-features", type=int, default=0)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--glm-path", default="auto", choices=["auto", "group", "simt", "tcgen05"])
+    ap.add_argument("--run-ahead", action="store_true",
+                    help="lock-step chains that finish a step early go on into the next step's rows (measured on C2: same job "
+                         "time -- the slowest chains are slow throughout -- and the idle tail moves into the last timed steps)")
     ap.add_argument("--skip-ess", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not time individual likelihood launches")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region")

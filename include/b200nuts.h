@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 
 enum b2_dtype { B2_F32 = 0, B2_F64 = 1 };
 
@@ -73,6 +73,10 @@ typedef struct b2_sampler_opts {
     int32_t hmc_jitter;         /* 1: step_rand = unif (hmc.py:26-27,104)                    */
     int32_t exec_mode;          /* b2_exec                                                   */
     int32_t glm_path;           /* b2_glm_path                                               */
+    int32_t run_ahead;          /* lock-step runs only: a chain that has finished this call's n_iters may go on
+                                   with up to run_ahead more transitions while slower chains catch up (the call
+                                   still returns as soon as EVERY chain has done n_iters); the trace buffers must
+                                   then hold n_iters + run_ahead rows.  0 = every chain stops at n_iters.        */
 } b2_sampler_opts;
 
 /* device trace: replaces NDArray.record per draw (backends/ndarray.py:258-277).

@@ -32,7 +32,7 @@ class SamplerOpts(C.Structure):
                 ("gamma", C.c_double), ("k", C.c_double), ("t0", C.c_double),
                 ("adapt_step_size", C.c_int32), ("adapt_mass", C.c_int32),
                 ("path_length", C.c_double), ("max_steps", C.c_int32), ("hmc_jitter", C.c_int32),
-                ("exec_mode", C.c_int32), ("glm_path", C.c_int32)]
+                ("exec_mode", C.c_int32), ("glm_path", C.c_int32), ("run_ahead", C.c_int32)]
 
 
 TRACE_FIELDS = ["d_q", "d_energy", "d_energy_error", "d_max_energy_error", "d_mean_tree_accept",

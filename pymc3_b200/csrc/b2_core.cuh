@@ -83,6 +83,7 @@ struct B2View {
     // sampler options
     int kind;                     // NUTS | HMC
     int iter_base, iter_end, tune_until;
+    int iter_cap;                 // a chain stops here: iter_end, or later when the run lets fast chains run ahead
     int max_treedepth, early_max_treedepth;
     double emax, target, gamma, k, t0;
     int adapt_step, adapt_mass;
@@ -496,7 +497,7 @@ B2_HD int b2_end_transition(const G& g, const B2View<T>& w, int c, B2ChainState&
         }
     }
     s.iter += 1;
-    if (s.iter >= w.iter_end) { s.phase = B2_PHASE_DONE; return B2_ACT_NONE; }
+    if (s.iter >= w.iter_cap) { s.phase = B2_PHASE_DONE; return B2_ACT_NONE; }
     return B2_ACT_BEGIN_TRANSITION;
 }
 
@@ -651,10 +652,10 @@ B2_HD bool b2_advance(const G& g, const B2View<T>& w, int c, B2ChainState& s, do
         s.cur_logp = logp_new;
         s.n_grad += 1;
         b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.V(B2_V_GE1, c));
-        if (s.iter >= w.iter_end) s.phase = B2_PHASE_DONE;
+        if (s.iter >= w.iter_cap) s.phase = B2_PHASE_DONE;
         else act = B2_ACT_BEGIN_TRANSITION;
     } else if (s.phase == B2_PHASE_RESUME) {              // continue from the last draw: no new gradient needed
-        if (s.iter >= w.iter_end) s.phase = B2_PHASE_DONE;
+        if (s.iter >= w.iter_cap) s.phase = B2_PHASE_DONE;
         else act = B2_ACT_BEGIN_TRANSITION;
     } else if (s.phase == B2_PHASE_TREE) {
         act = b2_finish_leaf(g, w, c, s, logp_new);

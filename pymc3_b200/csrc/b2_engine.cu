@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w, int 
 template <typename T, typename G>
 __device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const B2ModelData& m, int c, T* hot) {
     B2ChainState s = w.st[c];
-    if (s.phase == B2_PHASE_FAILED || (s.phase == B2_PHASE_DONE && s.iter >= w.iter_end)) return;
+    if (s.phase == B2_PHASE_FAILED || (s.phase == B2_PHASE_DONE && s.iter >= w.iter_cap)) return;
     if (hot) {
         for (int slot = 0; slot < B2_V_STACK0; ++slot) {
             const T* src = w.Vglobal(slot, c);
@@ -116,7 +116,7 @@ __device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const 
         g.sync();
         w.hot = hot;
     }
-    if (s.phase == B2_PHASE_DONE && s.iter < w.iter_end) {   // continuation run
+    if (s.phase == B2_PHASE_DONE && s.iter < w.iter_cap) {   // continuation run
         s.phase = B2_PHASE_RESUME;
         b2_advance<T, G>(g, w, c, s, 0.0);
     }
@@ -174,10 +174,11 @@ static int persistent_block_threads(const b2_engine* e) {
     return e->D >= 2048 ? 512 : 256;
 }
 
-__global__ void k_count_active(const B2ChainState* st, int C, int* out) {
+// chains that still owe transitions of this call (with run-ahead, faster chains are already past iter_end)
+__global__ void k_count_active(const B2ChainState* st, int C, int iter_end, int* out) {
     int n = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x)
-        n += b2_needs_grad(st[c].phase) ? 1 : 0;
+        n += (b2_needs_grad(st[c].phase) && st[c].iter < iter_end) ? 1 : 0;
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
 }
@@ -413,6 +414,7 @@ static B2View<T> build_view(b2_engine* e, const b2_sampler_opts* o, const b2_tra
     B2View<T> w = make_view<T>(e);
     w.kind = o->kind;
     w.iter_base = e->iter_done; w.iter_end = e->iter_done + o->n_iters; w.tune_until = o->tune_until;
+    w.iter_cap = w.iter_end;                      // run_t raises it for lock-step runs with run_ahead
     w.max_treedepth = o->max_treedepth; w.early_max_treedepth = o->early_max_treedepth;
     w.emax = o->Emax; w.target = o->target_accept; w.gamma = o->gamma; w.k = o->k; w.t0 = o->t0;
     w.adapt_step = o->adapt_step_size; w.adapt_mass = o->adapt_mass;
@@ -460,6 +462,8 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         const T* qA = w.V(B2_V_QE0, 0); const T* qB = w.V(B2_V_QE1, 0);
         T* gA = w.V(B2_V_GE0, 0); T* gB = w.V(B2_V_GE1, 0);
         const int batch = 32;
+        // fast chains may run ahead of this call's last iteration (rows exist in the caller's trace buffers)
+        if (o->run_ahead > 0) w.iter_cap = w.iter_end + o->run_ahead;
         // GLM on the tensor-core path: {tcgen05 likelihood, fused finalize+advance+repack} per step
         const bool fused_tc = sizeof(T) == 4 && !blk && e->md.family == B2_FAMILY_GLM_LOGIT &&
                               pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05 && !b2_glm_tcw_supported(e);
@@ -491,7 +495,7 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
                 if (e->profile) cudaEventRecord(e->ev[3 * b + 2], s);
             }
             B2_CUDA_OK(cudaMemsetAsync(e->d_active, 0, sizeof(int), s));
-            k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, e->d_active);
+            k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, w.iter_end, e->d_active);
             e->launches += 1;
             B2_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
             B2_CUDA_OK(cudaStreamSynchronize(s));
@@ -645,7 +649,7 @@ extern "C" int b2_step_active(b2_engine* e, int32_t* host_count, void* stream) {
     B2_CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = (cudaStream_t)stream;
     B2_CUDA_OK(cudaMemsetAsync(e->d_active, 0, sizeof(int), s));
-    k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, e->d_active);
+    k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, e->iter_done + e->step_opts.n_iters, e->d_active);
     e->launches += 1;
     B2_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
     B2_CUDA_OK(cudaStreamSynchronize(s));

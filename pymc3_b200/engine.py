@@ -125,10 +125,14 @@ class Engine:
                                     dtype={"f8": torch.float64, "i4": torch.int32, "u1": torch.uint8}[code])
         return out
 
-    def run(self, kind, n_iters, tune_until, opts, trace_q=True, out=None, row0=0):
+    def run(self, kind, n_iters, tune_until, opts, trace_q=True, out=None, row0=0, run_ahead=False):
         """Runs `n_iters` transitions of every chain; returns {'q': [n, C, D], stat: [n, C]} device
         tensors.  With `out` (from alloc_trace) the rows [row0, row0 + n_iters) of those buffers are
-        filled instead of allocating (chunked runs of one long job)."""
+        filled instead of allocating (chunked runs of one long job).  `run_ahead` (needs `out`): in
+        lock-step runs, chains that finish this chunk early go on into the following rows of `out`
+        instead of idling until the slowest chain of the chunk is done; the call still returns as
+        soon as every chain has completed the chunk, and the next chunk picks the chains up where
+        they are."""
         if out is None:
             out = self.alloc_trace(kind, n_iters, trace_q)
             view = out
@@ -139,6 +143,8 @@ class Engine:
             assert t.is_contiguous() and t.shape[0] == n_iters
             setattr(tr, "d_" + name, t.data_ptr())
         o = _capi.SamplerOpts(kind=kind, n_iters=int(n_iters), tune_until=int(tune_until), **opts)
+        if run_ahead and out is not view:
+            o.run_ahead = int(next(iter(out.values())).shape[0] - row0 - n_iters)
         _capi.check(self.lib.b2_sample_run(self.handle, C.byref(o), C.byref(tr), self._stream()), self.lib)
         self.iter_done += int(n_iters)
         return view

@@ -23,7 +23,7 @@ static int run_t(const B2ModelData& md, int C, const double* q0, const uint64_t*
     memset(&w, 0, sizeof(w));
     w.C = C; w.D = D; w.Dp = Dp; w.vec = vec.data(); w.wv_mean = wm.data(); w.wv_m2 = w2.data();
     w.st = st.data(); w.lv = lv.data(); w.logp_eval = lp.data(); w.hot = nullptr; w.lv_hot = nullptr; w.stk_hot = nullptr; w.stk_mask = 0; w.stk_idx = 0;
-    w.kind = o->kind; w.iter_base = 0; w.iter_end = o->n_iters; w.tune_until = o->tune_until;
+    w.kind = o->kind; w.iter_base = 0; w.iter_end = o->n_iters; w.iter_cap = o->n_iters; w.tune_until = o->tune_until;
     w.max_treedepth = o->max_treedepth; w.early_max_treedepth = o->early_max_treedepth;
     w.emax = o->Emax; w.target = o->target_accept; w.gamma = o->gamma; w.k = o->k; w.t0 = o->t0;
     w.adapt_step = o->adapt_step_size; w.adapt_mass = o->adapt_mass;

@@ -28,13 +28,13 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert set(names) == set(_capi.EXPORTS)
-    assert _capi.load_library().b2_abi_version() == 1
+    assert _capi.load_library().b2_abi_version() == 2
 
 
 def test_ctypes_structs_match_header_layout():
     """sizes the C compiler computes for the ABI structs (LP64): guards against field drift."""
     assert ctypes.sizeof(_capi.ModelDesc) == 16 + 6 * 8 + 32
-    assert ctypes.sizeof(_capi.SamplerOpts) == 5 * 4 + 4 + 5 * 8 + 2 * 4 + 8 + 4 * 4
+    assert ctypes.sizeof(_capi.SamplerOpts) == 5 * 4 + 4 + 5 * 8 + 2 * 4 + 8 + 5 * 4 + 4
     assert ctypes.sizeof(_capi.TraceOut) == 15 * 8
     assert ctypes.sizeof(_capi.ChainReport) == 6 * 4 + 8 + 16
 

@@ -320,6 +320,47 @@ def test_chunked_runs_continue_the_same_chains(exec_mode):
     eng.close()
 
 
+@pytest.mark.parametrize("which", ["eight_schools_f64", "glm_simt_f32", "glm_tcgen05_f32"])
+def test_run_ahead_chunks_equal_one_run(which):
+    """lock-step chunks with run_ahead: chains that finish a chunk early go on into the following rows of
+    the preallocated trace; the per-chain results are those of one uninterrupted run, bit for bit."""
+    from pymc3_b200 import model as pm
+    if which == "eight_schools_f64":
+        model, dtype, C = models_util.pairs()["eight_schools"][0], "float64", 37
+        D = 10
+        extra = {}
+    else:
+        X, y = models_util.glm_data(4000, 20, seed=21)
+        model, dtype, C, D = pm.LogisticGLM(X, y), "float32", 150, 21
+        extra = {"glm_path": _capi.B2_GLM_TCGEN05 if which == "glm_tcgen05_f32" else _capi.B2_GLM_SIMT}
+    q0 = np.random.default_rng(13).uniform(-1, 1, size=(C, D)) * 0.5
+    seeds = np.arange(C) + 70
+    one = _run_engine(model, q0, seeds, 45, 30, _capi.B2_NUTS, dtype, _capi.B2_EXEC_LOCKSTEP, **extra)
+    eng = model.engine(C, dtype=dtype)
+    eng.set_state(q0, seeds, 0.25 / D ** 0.25, np.zeros(D), np.ones(D), 10.0)
+    opts = dict(NUTS_OPTS)
+    opts.update(extra)
+    opts["exec_mode"] = _capi.B2_EXEC_LOCKSTEP
+    trace = eng.alloc_trace(_capi.B2_NUTS, 45)
+    ahead = []
+    for i in range(3):
+        eng.run(_capi.B2_NUTS, 15, 30, opts, out=trace, row0=15 * i, run_ahead=True)
+        ahead.append(max(r.iter for r in eng.reports()) - 15 * (i + 1))
+    got = {k: v.cpu().numpy() for k, v in trace.items()}
+    if which == "glm_tcgen05_f32":
+        # the tensor-core launch re-divides its grid over the live chain tiles, so the slab summation order (and
+        # the last bits) depend on which chains are live together: equal decisions early on, not bit-equal
+        assert (got["depth"][:8] == one["depth"][:8]).mean() > 0.97
+        assert np.abs(got["q"][:5] - one["q"][:5]).max() < 1e-3
+        assert np.isfinite(got["energy"]).all() and np.array_equal(got["tune"], one["tune"])
+    else:
+        for k in ("q", "depth", "tree_size", "energy", "step_size", "tune", "diverging"):
+            assert np.array_equal(got[k], one[k]), k
+    assert ahead[0] > 0 and ahead[2] == 0            # somebody ran ahead; nobody beyond the last row
+    assert all(r.iter == 45 and r.phase == _capi.PHASE_DONE for r in eng.reports())
+    eng.close()
+
+
 def test_fused_tensor_core_lockstep_agrees_with_simt_lockstep():
     """fp32 NUTS on a GLM big enough for the chain-batched kernels: the fused tcgen05 step
     ({likelihood, finalize+advance+repack}) against the SIMT path -- same decisions early on,
