@@ -53,6 +53,10 @@ typedef struct b2_model_desc {
 
 enum b2_kind { B2_NUTS = 0, B2_HMC = 1 };
 enum b2_exec { B2_EXEC_AUTO = 0, B2_EXEC_PERSISTENT = 1, B2_EXEC_LOCKSTEP = 2 };
+/* likelihood kernel of B2_GLM_LOGIT: GROUP = one warp/block per chain (small N); SIMT = chain-batched FFMA/DFMA
+   tiles (fp64 check build, any shape); TCGEN05 = tensor cores, fp32 build only: up to 127 features fused with the
+   lock-step companion kernel (b2_glm_tc.cu), 128..256 features the wide variant (b2_glm_tcw.cu).  AUTO picks
+   TCGEN05 where it applies. */
 enum b2_glm_path { B2_GLM_AUTO = 0, B2_GLM_GROUP = 1, B2_GLM_SIMT = 2, B2_GLM_TCGEN05 = 3 };
 
 /* ctor arguments of NUTS / HamiltonianMC / BaseHMC (nuts.py:105, hmc.py:53, base_hmc.py:41-59) */
