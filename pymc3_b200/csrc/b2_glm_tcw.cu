@@ -2,19 +2,21 @@
 // (config C5: K = 256 features + intercept; reference: pymc3/glm/linear.py:49-101, glm/families.py:115-119,
 // evaluated by ValueGradFunction.__call__, model.py:645-666).  Same algorithm as b2_glm_tc.cu
 //
-//   GEMM1  S[128 chains, 64 obs]    = Q . Xtile^T        (K up to 256: 16 K steps x 3 bf16 split passes)
+//   GEMM1  S[128 chains, 32 obs]    = Q . Xtile^T        (K up to 256: 16 K steps x 3 bf16 split passes)
 //   epi    R = y - sigmoid(S + q0),  logp += ...          (the intercept q0 is added here, not in the GEMM)
 //   GEMM2  G[128 chains, 128 feat] += R . Xtile[:, half]  (MN-major read of the SAME shared-memory tile)
 //
-// with the tensor-memory budget re-cut for twice the features.  512 TMEM columns hold S 64, R 64
+// with the tensor-memory budget re-cut for twice the features.  512 TMEM columns hold S 2x32, R 2x32
 // (bf16 hi | lo), Q 256 (bf16 hi | lo of 256 features) and ONE 128-feature half of G, so a CTA owns
 // (chain tile, observation slab, feature half): the two CTAs of a pair walk the same X tiles (second reader
 // hits L2), both run GEMM1 and the epilogue, each accumulates its half of the gradient.  Tensor work per
-// 64-observation tile and CTA: GEMM1 1536 + GEMM2 768 cycles against 1536 + 1536 for an (impossible) unsplit
-// CTA, i.e. 2/3 efficiency from the duplicated GEMM1.  S and R are single-buffered (no columns left): GEMM1 of
-// the next tile starts as soon as S is in registers, so the epilogue math still overlaps tensor work.
-// (A first version used 32-observation tiles with double buffers; its 54 small MMAs per tile cost ~35 cycles each
-// whatever their N, 2.8 k cycles per 32 observations -- this one issues 60 per 64.)
+// 32-observation tile and CTA: GEMM1 768 + GEMM2 384 cycles against 768 + 768 for an (impossible) unsplit
+// CTA, i.e. 2/3 efficiency from the duplicated GEMM1.
+// A tile is 32 observations so that a pipeline stage stays one 32 KB bulk copy (+128 B of y) and S / R can be
+// double-buffered; its 54 MMAs are small (N = 32: 16 cycles of tensor work), so the issue loop must be cheap:
+// descriptors are `per-tile base + constant` (see mma_ts_split), the K-step count is a template parameter.
+// (Measured, 3 M rows x 256 chains: 3.74 ms with 64-bit descriptors rebuilt per MMA (~35 cycles per MMA whatever
+// its N), 2.89 ms for a 64-observation single-buffered variant, 2.67 ms for this one.)
 // The intercept never enters the GEMMs (K = 256 would become 257): eta = S + q0 in the epilogue, and its
 // gradient is the row sum of R, accumulated next to logp.  Zero-padded rows carry y = -1 and are masked.
 #include <cstring>
@@ -23,20 +25,20 @@
 #include "b2_tc_ptx.cuh"
 
 #define TW_CHAINS 128
-#define TW_OBS 64
+#define TW_OBS 32
 #define TW_KP 256
-#define TW_STAGES 3
-#define TW_XPART_BYTES (TW_OBS * TW_KP * 2)             // 32768: one of {hi, lo}, four 64-column atoms of 64 rows
-#define TW_Y_BYTES (TW_OBS * 4)                         // 256
-#define TW_STAGE_DATA (2 * TW_XPART_BYTES + TW_Y_BYTES) // 65792 in global memory: Xhi | Xlo | y
+#define TW_STAGES 6
+#define TW_XPART_BYTES (TW_OBS * TW_KP * 2)             // 16384: one of {hi, lo}, four 64-column atoms of 32 rows
+#define TW_Y_BYTES (TW_OBS * 4)                         // 128
+#define TW_STAGE_DATA (2 * TW_XPART_BYTES + TW_Y_BYTES) // 32896 in global memory: Xhi | Xlo | y
 #define TW_STAGE_BYTES (2 * TW_XPART_BYTES)
 #define TW_SMEM_BYTES (1024 + TW_STAGES * (TW_STAGE_BYTES + TW_Y_BYTES) + 512)
-#define TW_EPI_GROUPS 4                                 // epilogue warpgroups; group g owns observation columns 16g..16g+15 of a tile
+#define TW_EPI_GROUPS 4                                 // epilogue warpgroups; group g takes tiles t = g (mod 4)
 #define TW_EPI_WARPS (4 * TW_EPI_GROUPS)
 #define TW_THREADS (128 + 32 * TW_EPI_WARPS)
 #define TW_TMEM_COLS 512
-#define TW_COL_S 0                                      // 64 columns
-#define TW_COL_P 64                                     // R: hi 32 cols | lo 32 cols
+#define TW_COL_S 0                                      // S[b] at 32 b
+#define TW_COL_P 64                                     // R[b] at 64 + 32 b: hi 16 cols | lo 16 cols
 #define TW_COL_G 128                                    // 128 columns (this CTA's feature half)
 #define TW_COL_Q 256                                    // hi 128 cols | lo 128 cols
 
@@ -94,6 +96,20 @@ __global__ void k_glm_tcw_compact(const B2ChainState* st, int n_chains, int* cnt
     chain_of_slot[atomicAdd(cnt, 1)] = c;
 }
 
+// GEMM1 of one tile for a compile-time number of live K steps: 3 split passes (Qhi.Xhi, Qlo.Xhi, Qhi.Xlo), fully
+// unrolled, one uniform add per MMA (descriptor low word = per-tile base + constant)
+template <int KS>
+__device__ __forceinline__ void tw_issue_gemm1(uint32_t d, uint32_t tmem, uint32_t dlo, uint32_t dhi, uint32_t idesc) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t qa = tmem + TW_COL_Q + (pass == 1 ? 128 : 0);
+#pragma unroll
+        for (int j = 0; j < KS; ++j)
+            mma_ts_split(d, qa + j * 8, dlo + (((pass == 2 ? TW_XPART_BYTES : 0) + (j >> 2) * (TW_OBS * 128) + (j & 3) * 32) >> 4),
+                         dhi, idesc, (pass > 0 || j > 0) ? 1u : 0u);
+    }
+}
+
 __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -103,13 +119,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
     uint64_t* q_full = bars;                       // 1
     uint64_t* x_full = bars + 1;                   // TW_STAGES
     uint64_t* x_empty = x_full + TW_STAGES;        // TW_STAGES
-    // every barrier is waited on by one set of agents walking its phases in order (a waiter that starts on a
-    // fresh barrier with parity 1 falls straight through: the phase "before" phase 0 counts as complete)
-    uint64_t* s_full = x_empty + TW_STAGES;        // 1
-    uint64_t* s_empty = s_full + 1;                // 1
-    uint64_t* p_full = s_empty + 1;                // 1
-    uint64_t* p_empty = p_full + 1;                // 1
-    uint64_t* g_full = p_empty + 1;                // 1
+    // S and R are double-buffered (b = t & 1) but their barriers are per tile-mod-4 (= per epilogue group): a
+    // barrier must only ever be waited on by one agent walking its phases in order -- a group that starts on a
+    // fresh barrier with parity 1 falls straight through (the phase "before" phase 0 counts as complete).
+    uint64_t* s_full = x_empty + TW_STAGES;        // 4
+    uint64_t* s_empty = s_full + 4;                // 4
+    uint64_t* p_full = s_empty + 4;                // 4
+    uint64_t* p_empty = p_full + 4;                // 4
+    uint64_t* g_full = p_empty + 4;                // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,7 +141,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, TW_EPI_WARPS);
         for (int i = 0; i < TW_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
-        mbar_init(s_full, 1); mbar_init(s_empty, TW_EPI_WARPS); mbar_init(p_full, TW_EPI_WARPS); mbar_init(p_empty, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 4); mbar_init(p_full + i, 4); mbar_init(p_empty + i, 1); }
         mbar_init(g_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -138,7 +155,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer: the X tile ring (one 64 KB + one 256 B bulk copy per stage)
+        // ===== producer: the X tile ring (one 32 KB + one 128 B bulk copy per stage)
         if (lane == 0) {
             for (int t = 0; t < T; ++t) {
                 const int s = t % TW_STAGES;
@@ -154,29 +171,25 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
         mbar_wait(q_full, 0, ws.err, 2);
         tc_fence_after();
         const int ks = (ws.K + 15) >> 4;                           // <= 16
-        const uint32_t idesc_g1 = TC_IDESC_BASE | ((TW_OBS >> 3) << 17) | ((TW_CHAINS >> 4) << 24);   // N = 64, K-major B
+        const uint32_t idesc_g1 = TC_IDESC_BASE | ((TW_OBS >> 3) << 17) | ((TW_CHAINS >> 4) << 24);   // N = 32, K-major B
         for (int t = 0; t < T; ++t) {
-            const int s = t % TW_STAGES;
+            const int s = t % TW_STAGES, b = t & 1;
             mbar_wait(x_full + s, (t / TW_STAGES) & 1, ws.err, 3);
-            if (t >= 1) mbar_wait(s_empty, (t - 1) & 1, ws.err, 4);      // S of tile t-1 is in registers
+            if (t >= 2) mbar_wait(s_empty + ((t - 2) & 3), ((t - 2) >> 2) & 1, ws.err, 4);   // S[b] of tile t-2 is in registers
             tc_fence_after();
             const uint32_t x_addr = smem_u32(x_s + s * TW_STAGE_BYTES);
-            const uint32_t d = tmem + TW_COL_S;
+            const uint32_t d = tmem + TW_COL_S + 32 * b;
             if (elect_one()) {
-                uint32_t acc = 0;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {              // Qhi.Xhi, Qlo.Xhi, Qhi.Xlo
-                    const uint32_t qa = tmem + TW_COL_Q + (pass == 1 ? 128 : 0);
-                    const uint32_t xa = x_addr + (pass == 2 ? TW_XPART_BYTES : 0);
-#pragma unroll
-                    for (int j = 0; j < TW_KP / 16; ++j) {
-                        if (j >= ks) break;
-                        const uint64_t bd = make_desc(xa + (j >> 2) * (TW_OBS * 128) + (j & 3) * 32, 16, 1024);
-                        mma_ts(d, qa + j * 8, bd, idesc_g1, acc);
-                        acc = 1;
-                    }
+                // descriptors: low word = per-tile base + compile-time offset, high word constant
+                const uint32_t dlo = tc_desc_lo(x_addr, 16), dhi = tc_desc_hi(1024);
+                switch ((ks + 1) >> 1) {                             // 8..16 live K steps, rounded up to even (zero columns)
+                    case 8: tw_issue_gemm1<16>(d, tmem, dlo, dhi, idesc_g1); break;
+                    case 7: tw_issue_gemm1<14>(d, tmem, dlo, dhi, idesc_g1); break;
+                    case 6: tw_issue_gemm1<12>(d, tmem, dlo, dhi, idesc_g1); break;
+                    case 5: tw_issue_gemm1<10>(d, tmem, dlo, dhi, idesc_g1); break;
+                    default: tw_issue_gemm1<8>(d, tmem, dlo, dhi, idesc_g1); break;
                 }
-                tc_commit(s_full);
+                tc_commit(s_full + (t & 3));
             }
             __syncwarp();
         }
@@ -187,32 +200,31 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
         const uint32_t n2 = (uint32_t)((kh + 15) & ~15);
         const uint32_t idesc_g2 = TC_IDESC_BASE | (1u << 16) | ((n2 >> 3) << 17) | ((TW_CHAINS >> 4) << 24);
         for (int u = 0; u < T; ++u) {
-            const int s = u % TW_STAGES;
-            mbar_wait(p_full, u & 1, ws.err, 5);
+            const int s = u % TW_STAGES, b = u & 1;
+            mbar_wait(p_full + (u & 3), (u >> 2) & 1, ws.err, 5);
             tc_fence_after();
             const uint32_t x_addr = smem_u32(x_s + s * TW_STAGE_BYTES) + half * 2 * (TW_OBS * 128);
-            const uint32_t p_base = tmem + TW_COL_P;
+            const uint32_t p_base = tmem + TW_COL_P + 32 * b;
             const uint32_t d = tmem + TW_COL_G;
             if (elect_one()) {
+                // MN-major B: 64-feature atoms LBO = 4096 B apart, 8-row groups SBO = 1024 B apart
+                const uint32_t dlo = tc_desc_lo(x_addr, TW_OBS * 128), dhi = tc_desc_hi(1024);
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {              // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
-                    const uint32_t pa = p_base + (pass == 1 ? 32 : 0);
-                    const uint32_t xa = x_addr + (pass == 2 ? TW_XPART_BYTES : 0);
+                    const uint32_t pa = p_base + (pass == 1 ? 16 : 0);
 #pragma unroll
-                    for (int j = 0; j < TW_OBS / 16; ++j) {
-                        // MN-major B: 64-feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
-                        const uint64_t bd = make_desc(xa + j * 2048, TW_OBS * 128, 1024);
-                        mma_ts(d, pa + j * 8, bd, idesc_g2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
-                    }
+                    for (int j = 0; j < TW_OBS / 16; ++j)
+                        mma_ts_split(d, pa + j * 8, dlo + (((pass == 2 ? TW_XPART_BYTES : 0) + j * 2048) >> 4), dhi, idesc_g2,
+                                     (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
                 }
                 tc_commit(x_empty + s);
-                tc_commit(p_empty);
+                tc_commit(p_empty + (u & 3));
                 if (u == T - 1) tc_commit(g_full);
             }
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ===== epilogue warpgroups: thread == (chain row, 16-observation column group)
+        // ===== epilogue warpgroups: thread == chain row; group cg owns every 4th tile (32 observation columns)
         const int wq = warp & 3;                                     // TMEM lane quarter this warp may touch
         const int cg = (warp - 4) >> 2;
         const int row = wq * 32 + lane;
@@ -249,59 +261,68 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             if (lane == 0) mbar_arrive(q_full);
         }
         float lp_sum = 0.f, lp_comp = 0.f, r_sum = 0.f, r_comp = 0.f;   // Kahan: no fp64 in the tile loop
-        for (int t = 0; t < T; ++t) {
-            const int s = t % TW_STAGES;
-            const float4* ys4 = reinterpret_cast<const float4*>(y_s + s * TW_Y_BYTES) + 4 * cg;
-            mbar_wait(x_full + s, (t / TW_STAGES) & 1, ws.err, 9);    // y values of this stage (async-proxy writes)
-            mbar_wait(s_full, t & 1, ws.err, 6);
+        for (int t = cg; t < T; t += TW_EPI_GROUPS) {
+            const int s = t % TW_STAGES, b = t & 1;
+            const float4* ys4 = reinterpret_cast<const float4*>(y_s + s * TW_Y_BYTES);
+            mbar_wait(s_full + cg, (t >> 2) & 1, ws.err, 6);
+            // y values of this stage: the phase is already complete (GEMM1 of this tile consumed the stage) and the
+            // next one cannot complete before this tile's R is handed to GEMM2, so the parity test is unambiguous
+            mbar_wait(x_full + s, (t / TW_STAGES) & 1, ws.err, 9);
             tc_fence_after();
-            uint32_t v[16];
-            TC_LD16(tmem + lane_addr + TW_COL_S + 16 * cg, v);
+            uint32_t v[2][16];
+            TC_LD16(tmem + lane_addr + TW_COL_S + 32 * b, v[0]);
+            TC_LD16(tmem + lane_addr + TW_COL_S + 32 * b + 16, v[1]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);                     // S(t) is in registers: GEMM1(t+1) may overwrite it
-            uint32_t hi[8], lo[8];
+            if (lane == 0) mbar_arrive(s_empty + cg);                // S(t) is in registers
+            uint32_t hi[2][8], lo[2][8];
             float lsum = 0.f, rsum = 0.f;
-            float yv[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 y4 = ys4[i];
-                yv[4 * i] = y4.x; yv[4 * i + 1] = y4.y; yv[4 * i + 2] = y4.z; yv[4 * i + 3] = y4.w;
-            }
+            for (int hh = 0; hh < 2; ++hh) {
+                float yv[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float r2[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float eta = __uint_as_float(v[2 * i + h]) + q0;
-                    const float yy = yv[2 * i + h];
-                    const bool valid = yy >= 0.f;
-                    const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
-                    const float w1 = 1.f + e;
-                    const float inv = tc_rcp(w1);
-                    const float sig = eta >= 0.f ? inv : e * inv;
-                    if (half == 0) {                             // logp is counted by one CTA of the pair
-                        const float term = fmaf(yy, eta, -fmaf(0.6931471805599453f, tc_lg2(w1), fmaxf(eta, 0.f)));
-                        lsum += valid ? term : 0.f;
-                    }
-                    r2[h] = valid ? yy - sig : 0.f;
-                    rsum += r2[h];
+                for (int i = 0; i < 4; ++i) {
+                    const float4 y4 = ys4[4 * hh + i];
+                    yv[4 * i] = y4.x; yv[4 * i + 1] = y4.y; yv[4 * i + 2] = y4.z; yv[4 * i + 3] = y4.w;
                 }
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
-                const float2 back = __bfloat1622float2(h2);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
-                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float r2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float eta = __uint_as_float(v[hh][2 * i + h]) + q0;
+                        const float yy = yv[2 * i + h];
+                        const bool valid = yy >= 0.f;
+                        const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
+                        const float w1 = 1.f + e;
+                        const float inv = tc_rcp(w1);
+                        const float sig = eta >= 0.f ? inv : e * inv;
+                        if (half == 0) {                             // logp is counted by one CTA of the pair
+                            const float term = fmaf(yy, eta, -fmaf(0.6931471805599453f, tc_lg2(w1), fmaxf(eta, 0.f)));
+                            lsum += valid ? term : 0.f;
+                        }
+                        r2[h] = valid ? yy - sig : 0.f;
+                        rsum += r2[h];
+                    }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[0], r2[1]);
+                    const float2 back = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r2[0] - back.x, r2[1] - back.y);
+                    hi[hh][i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[hh][i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
             }
-            if (t >= 1) mbar_wait(p_empty, (t - 1) & 1, ws.err, 7);  // GEMM2 of tile t-1 has read R
+            if (t >= 2) mbar_wait(p_empty + ((t - 2) & 3), ((t - 2) >> 2) & 1, ws.err, 7);   // GEMM2 of tile t-2 has read R[b]
             tc_fence_after();
-            TC_ST8(tmem + lane_addr + TW_COL_P + 8 * cg, hi);
-            TC_ST8(tmem + lane_addr + TW_COL_P + 32 + 8 * cg, lo);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                TC_ST8(tmem + lane_addr + TW_COL_P + 32 * b + 8 * hh, hi[hh]);
+                TC_ST8(tmem + lane_addr + TW_COL_P + 32 * b + 16 + 8 * hh, lo[hh]);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
+            if (lane == 0) mbar_arrive(p_full + cg);
             float ky = lsum - lp_comp, kt = lp_sum + ky;
             lp_comp = (kt - lp_sum) - ky; lp_sum = kt;
             ky = rsum - r_comp; kt = r_sum + ky;

@@ -76,6 +76,22 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// Same MMA with the shared-memory descriptor passed as its two 32-bit halves: inside an unrolled issue loop the
+// low word is `base + constant` (one uniform add per MMA) and the high word never changes.  Building the full
+// 64-bit descriptor per MMA cost a 4-deep dependent chain of uniform-datapath ops (~35 cycles per MMA, more than
+// the 16-32 cycles of tensor work of an N = 32..64 MMA).
+__device__ __forceinline__ void mma_ts_split(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t tc_desc_hi(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
 // shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
