@@ -244,25 +244,28 @@ B2_HD bool b2_uturn(const G& g, int D, const T* var,
                     const T* first1, const T* last1, const T* psum1,
                     const T* first2, const T* last2, const T* psum2,
                     bool extra, T* out_psum, T* out_plast) {
-    double d[6] = {0, 0, 0, 0, 0, 0};
+    // a lane's few components are summed in the vector dtype (only the signs of the totals matter), the
+    // cross-lane reduction is fp64 like every other reduction
+    T part[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
     for (int i = g.lane(); i < D; i += G::NT) {
         const T vr = var[i];
         const T f1 = first1[i], l1 = last1[i], s1 = psum1[i];
         const T f2 = first2[i], l2 = last2[i], s2 = psum2[i];
         const T tot = s1 + s2;
-        d[0] += (double)(tot * (vr * f1));
-        d[1] += (double)(tot * (vr * l2));
+        part[0] += tot * (vr * f1);
+        part[1] += tot * (vr * l2);
         if (extra) {
             const T a = s1 + f2;
-            d[2] += (double)(a * (vr * f1));
-            d[3] += (double)(a * (vr * f2));
+            part[2] += a * (vr * f1);
+            part[3] += a * (vr * f2);
             const T b = l1 + s2;
-            d[4] += (double)(b * (vr * l1));
-            d[5] += (double)(b * (vr * l2));
+            part[4] += b * (vr * l1);
+            part[5] += b * (vr * l2);
         }
         if (out_psum) out_psum[i] = tot;
         if (out_plast) out_plast[i] = l2;
     }
+    double d[6] = {(double)part[0], (double)part[1], (double)part[2], (double)part[3], (double)part[4], (double)part[5]};
     g.allsum(d);
     bool turning = (d[0] <= 0) || (d[1] <= 0);
     if (extra) turning = turning || (d[2] <= 0) || (d[3] <= 0) || (d[4] <= 0) || (d[5] <= 0);
