@@ -299,12 +299,13 @@ B2_HD double b2_finish_leapfrog(const G& g, const B2View<T>& w, int c, int e, do
     const T* gr = w.V(B2_V_GE0 + e, c);
     const T* var = w.V(B2_V_VAR, c);
     const T half = (T)(0.5 * eps_signed);
-    double kin[1] = {0.0};
+    T part = (T)0;                                        // a lane's few components in the vector dtype, lanes in fp64
     for (int i = g.lane(); i < w.D; i += G::NT) {
         const T pn = p[i] + half * gr[i];
         p[i] = pn;
-        kin[0] += (double)(pn * (var[i] * pn));
+        part += pn * (var[i] * pn);
     }
+    double kin[1] = {(double)part};
     g.allsum(kin);
     return 0.5 * kin[0] - logp;
 }
