@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.run([nvcc, "-shared", "-o", SO] + objs + ["-lcuda"], check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs + ["-lcuda"], check=True)
     return SO
 
 
