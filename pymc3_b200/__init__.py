@@ -11,6 +11,7 @@ include/b200nuts.h (pymc3_b200/_capi.py).  There is no CPU fallback.
 __version__ = "0.1.0"
 
 from . import glm, stats  # noqa: F401
+# stats_device (torch tensor ops on the device trace) is imported on demand: `from pymc3_b200 import stats_device`
 from .backends import MultiTrace, NDArray, load_trace, merge_traces, save_trace  # noqa: F401
 from .exceptions import ParallelSamplingError, SamplingError  # noqa: F401
 from .model import (EightSchoolsNCP, HierLinearNCP, LogisticGLM, Model, StdNormal, StochVol,  # noqa: F401

@@ -249,3 +249,27 @@ def test_resume_from_existing_trace():
     assert len(more) == 65 and more.nchains == 3
     assert np.array_equal(more.get_values("x", chains=1)[:40], first.get_values("x", chains=1))
     assert more.get_sampler_stats("depth", chains=0).shape == (65,)
+
+
+def test_device_diagnostics_match_host_diagnostics_on_a_real_trace():
+    """bulk ESS / R-hat computed on the device trace (no host copy) == the NumPy estimators"""
+    import torch
+    from pymc3_b200 import _capi, stats_device
+    model = pm.EightSchoolsNCP()
+    C, D = 32, 10
+    eng = model.engine(C, dtype="float32")
+    eng.set_state(np.random.default_rng(3).uniform(-1, 1, size=(C, D)), np.arange(C) + 7, 0.25 / D ** 0.25,
+                  np.zeros(D), np.ones(D), 10.0)
+    opts = dict(max_treedepth=10, early_max_treedepth=8, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75, t0=10.0,
+                adapt_step_size=1, adapt_mass=1, path_length=2.0, max_steps=1024, hmc_jitter=0, exec_mode=0, glm_path=0)
+    out = eng.run(_capi.B2_NUTS, 500, 250, opts)
+    q = out["q"][250:]                                                # [draws, chains, D] on the GPU
+    assert q.is_cuda
+    x = stats_device.from_trace(q)
+    ess_d, rhat_d = stats_device.ess_bulk(x), stats_device.rhat(x)
+    assert ess_d.is_cuda and rhat_d.is_cuda
+    host = x.cpu().numpy()
+    np.testing.assert_allclose(ess_d.cpu().numpy(), pm.stats.ess(host), rtol=1e-7)
+    np.testing.assert_allclose(rhat_d.cpu().numpy(), pm.stats.rhat(host), rtol=1e-9)
+    assert float(rhat_d.max()) < 1.05 and float(ess_d.min()) > 1000
+    eng.close()
