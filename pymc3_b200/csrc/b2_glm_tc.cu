@@ -17,10 +17,13 @@
 // build into the exact 128B-swizzled shared-memory image the UMMA descriptors expect, so a pipeline
 // stage is one contiguous 32 KB copy (+256 B of y) and no tensor map is needed.  Q (the positions) is
 // split to bf16 hi/lo by the epilogue warps and written straight into TMEM.  Accumulators live in TMEM
-// (S double-buffered 2x64 cols, R 2x64 cols, G 128 cols).  Warp roles: 0 = bulk-copy producer,
-// 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..19 = four epilogue warpgroups (TMEM lane ==
-// chain; warpgroup g takes observation columns 16g..16g+15 of every tile, so each SM sub-partition
-// always has four epilogue warps to interleave -- one warp per scheduler was latency-bound, ncu r1).
+// (S double-buffered 2x64 cols, R 2x64 cols, G 128 cols, Q 128 cols).  Warp roles: 0 = bulk-copy producer,
+// 1 = GEMM1 issuer, 3 = GEMM2 issuer (the whole warp runs the uniform loop, one elected lane issues),
+// 2 = TMEM allocator, 4..19 = four epilogue warpgroups (TMEM lane == chain).  Warpgroups {0,1} take even tiles and
+// {2,3} odd tiles, 32 observation columns per warp and tile, so each SM sub-partition always has four epilogue
+// warps to interleave and the two pairs run one tile apart (one warp per scheduler was latency-bound, ncu r1;
+// all sixteen marching through the same tile left the MUFU and TMEM phases unoverlapped, ncu r1b).
+// Only the K steps / N columns that hold real features are issued (7 of 8 K steps, N = 112 at D + 1 = 101).
 #include <cuda_bf16.h>
 #include <cstring>
 #include <cstdlib>
