@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 2
+#define B2_ABI_VERSION 3
 
 enum b2_dtype { B2_F32 = 0, B2_F64 = 1 };
 
@@ -132,6 +132,15 @@ int b2_engine_destroy(b2_engine* e);
  * d_q [n_points, D] (engine dtype) -> d_logp [n_points] (double), d_grad [n_points, D]. */
 int b2_logp_dlogp(b2_engine* e, const void* d_q, int32_t n_points, double* d_logp, void* d_grad,
                   int32_t glm_path, void* stream);
+
+/* replaces CpuLeapfrogIntegrator.compute_state followed by n_steps x CpuLeapfrogIntegrator.step(epsilon, state)
+ * (integration.py:39-47, 49-109) with a static diagonal potential (QuadPotentialDiag.velocity / .energy,
+ * quadpotential.py:356-397), for all n_chains chains at once: d_q, d_p [C, D] (engine dtype) -> d_q_out, d_p_out
+ * [C, D] and d_energy_out [C] (may be NULL) = kinetic - logp of the end state; d_var [D] is the diagonal of M^-1
+ * (velocity = var * p).  epsilon may be negative (time reversal, tests/test_hmc.py:27-46).  Uses the engine's
+ * edge slots and mass diagonal as scratch: call b2_set_state again before sampling. */
+int b2_leapfrog(b2_engine* e, const void* d_q, const void* d_p, const double* d_var, double epsilon,
+                int32_t n_steps, void* d_q_out, void* d_p_out, double* d_energy_out, int32_t glm_path, void* stream);
 
 /* replaces per-chain seeding + start points + init_nuts' potential
  * (sampling.py:410-413, 883-884, 1915-1929; base_hmc.py:93-103):

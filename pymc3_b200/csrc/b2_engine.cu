@@ -480,14 +480,15 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         for (;;) {
             for (int b = 0; b < batch; ++b) {
                 if (e->profile) cudaEventRecord(e->ev[3 * b], s);
-                int rc = fused_tc ? b2_glm_tc_main(e, s)
-                                  : launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
-                if (rc) return rc;
-                if (e->profile) cudaEventRecord(e->ev[3 * b + 1], s);
                 if (fused_tc) {
-                    rc = b2_glm_tc_post(e, &w, s);
+                    // likelihood + state machine of both halves (b2_glm_tc.cu); the events split the two only in
+                    // the two-kernel schedule
+                    int rc = b2_glm_tc_step(e, &w, s, e->profile ? e->ev[3 * b + 1] : (cudaEvent_t)0);
                     if (rc) return rc;
                 } else {
+                    int rc = launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
+                    if (rc) return rc;
+                    if (e->profile) cudaEventRecord(e->ev[3 * b + 1], s);
                     if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 0);
                     else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 0);
                     e->launches += 1;
@@ -514,19 +515,115 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
     return 0;
 }
 
-extern "C" int b2_sample_run(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* trace, void* stream) {
-    if (!e || !o) { b2_set_error("b2_sample_run: null argument"); return -1; }
-    if (!e->state_set) { b2_set_error("b2_sample_run: call b2_set_state first"); return -2; }
-    if (o->n_iters <= 0) { b2_set_error("b2_sample_run: n_iters must be > 0"); return -3; }
-    if (o->kind != B2_NUTS && o->kind != B2_HMC) { b2_set_error("b2_sample_run: unknown sampler kind"); return -4; }
+// argument checks shared by b2_sample_run and b2_step_begin (the stepwise path runs the same state machine)
+static int check_run_args(const char* who, const b2_engine* e, const b2_sampler_opts* o) {
+    const std::string w(who);
+    if (!e || !o) { b2_set_error(w + ": null argument"); return -1; }
+    if (!e->state_set) { b2_set_error(w + ": call b2_set_state first"); return -2; }
+    if (o->n_iters <= 0) { b2_set_error(w + ": n_iters must be > 0"); return -3; }
+    if (o->kind != B2_NUTS && o->kind != B2_HMC) { b2_set_error(w + ": unknown sampler kind"); return -4; }
     if (o->kind == B2_NUTS && (o->max_treedepth < 1 || o->max_treedepth > B2_MAX_LEVELS ||
                                o->early_max_treedepth < 1 || o->early_max_treedepth > B2_MAX_LEVELS)) {
-        b2_set_error("b2_sample_run: tree depths must be in [1, 12]");
+        b2_set_error(w + ": tree depths must be in [1, 12]");     // slot_map holds 12 nibbles, B2_MAX_LEVELS stack buffers
         return -5;
     }
+    if (o->kind == B2_HMC && o->max_steps < 1) { b2_set_error(w + ": max_steps must be >= 1"); return -5; }
+    return 0;
+}
+
+extern "C" int b2_sample_run(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* trace, void* stream) {
+    const int rc = check_run_args("b2_sample_run", e, o);
+    if (rc) return rc;
+    if (e->stepping) { b2_set_error("b2_sample_run: a stepwise run is in progress (b2_step_end first)"); return -6; }
     B2_CUDA_OK(cudaSetDevice(e->device));
     return e->dtype == B2_F64 ? run_t<double>(e, o, trace, (cudaStream_t)stream)
                               : run_t<float>(e, o, trace, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ leapfrog integrator hook
+// CpuLeapfrogIntegrator.compute_state + n x .step(epsilon, state) (integration.py:39-47, 49-109) for every
+// chain at once, with a static diagonal potential `var` (QuadPotentialDiag, quadpotential.py:356-397).  It runs
+// the very device functions the samplers use (b2_prepare_leapfrog / b2_finish_leapfrog + the family's
+// likelihood kernel), so the reference's reversibility test (tests/test_hmc.py:27-46) and the oracle's
+// Leapfrog.step can be held against the product's integrator directly.
+enum { B2_LF_LOAD = 0, B2_LF_PREPARE = 1, B2_LF_FINISH = 2, B2_LF_STORE = 3 };
+
+template <typename T, typename G>
+__device__ __forceinline__ void lf_body(const G& g, const B2View<T>& w, int c, int op, double eps, const T* q_in,
+                                        const T* p_in, const double* var, T* q_out, T* p_out, double* energy) {
+    if (op == B2_LF_LOAD) {
+        T *q = w.V(B2_V_QE0, c), *p = w.V(B2_V_PE0, c), *vr = w.V(B2_V_VAR, c);
+        for (int i = g.lane(); i < w.D; i += G::NT) {
+            q[i] = q_in[(size_t)c * w.D + i]; p[i] = p_in[(size_t)c * w.D + i]; vr[i] = (T)var[i];
+        }
+    } else if (op == B2_LF_PREPARE) {
+        b2_prepare_leapfrog<T, G>(g, w, c, 0, eps);
+    } else if (op == B2_LF_FINISH) {
+        const double en = b2_finish_leapfrog<T, G>(g, w, c, 0, eps, w.logp_eval[c]);
+        if (g.lane() == 0 && energy) energy[c] = en;
+    } else {
+        const T *q = w.V(B2_V_QE0, c), *p = w.V(B2_V_PE0, c);
+        for (int i = g.lane(); i < w.D; i += G::NT) { q_out[(size_t)c * w.D + i] = q[i]; p_out[(size_t)c * w.D + i] = p[i]; }
+    }
+}
+
+template <typename T>
+__global__ void k_lf_warp(B2View<T> w, int op, double eps, const T* q_in, const T* p_in, const double* var, T* q_out,
+                          T* p_out, double* energy) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= w.C) return;
+    B2WarpGroup g;
+    lf_body<T, B2WarpGroup>(g, w, c, op, eps, q_in, p_in, var, q_out, p_out, energy);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B2_BLOCK_NT) k_lf_block(B2View<T> w, int op, double eps, const T* q_in, const T* p_in,
+                                                          const double* var, T* q_out, T* p_out, double* energy) {
+    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
+    B2BlockGroup<B2_BLOCK_NT> g;
+    g.red = red;
+    lf_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, blockIdx.x, op, eps, q_in, p_in, var, q_out, p_out, energy);
+}
+
+template <typename T>
+static int leapfrog_t(b2_engine* e, const void* d_q, const void* d_p, const double* d_var, double eps, int n_steps,
+                      void* d_q_out, void* d_p_out, double* d_energy, int glm_path, cudaStream_t s) {
+    B2View<T> w = make_view<T>(e);
+    const bool blk = use_block_group(e);
+    const int nb = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
+    auto phase = [&](int op, double ee) {
+        if (blk) k_lf_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, op, ee, (const T*)d_q, (const T*)d_p, d_var, (T*)d_q_out, (T*)d_p_out, d_energy);
+        else k_lf_warp<T><<<nb, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, op, ee, (const T*)d_q, (const T*)d_p, d_var, (T*)d_q_out, (T*)d_p_out, d_energy);
+        e->launches += 1;
+    };
+    const T* qA = w.V(B2_V_QE0, 0);
+    T* gA = w.V(B2_V_GE0, 0);
+    phase(B2_LF_LOAD, 0.0);
+    int rc = launch_likelihood<T>(e, qA, qA, gA, gA, e->Dp, nullptr, e->C, e->logp_eval, glm_path, s);   // compute_state
+    if (rc) return rc;
+    if (n_steps == 0) phase(B2_LF_FINISH, 0.0);           // energy of the start state (no kick)
+    for (int i = 0; i < n_steps; ++i) {
+        phase(B2_LF_PREPARE, eps);
+        rc = launch_likelihood<T>(e, qA, qA, gA, gA, e->Dp, nullptr, e->C, e->logp_eval, glm_path, s);
+        if (rc) return rc;
+        phase(B2_LF_FINISH, eps);
+    }
+    phase(B2_LF_STORE, 0.0);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2_leapfrog(b2_engine* e, const void* d_q, const void* d_p, const double* d_var, double epsilon,
+                           int32_t n_steps, void* d_q_out, void* d_p_out, double* d_energy_out, int32_t glm_path,
+                           void* stream) {
+    if (!e || !d_q || !d_p || !d_var || !d_q_out || !d_p_out) { b2_set_error("b2_leapfrog: null argument"); return -1; }
+    if (n_steps < 0) { b2_set_error("b2_leapfrog: n_steps must be >= 0"); return -2; }
+    if (e->stepping) { b2_set_error("b2_leapfrog: a stepwise run is in progress"); return -3; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    e->state_set = false;                  // the edge slots and the mass diagonal were overwritten: b2_set_state before sampling
+    return e->dtype == B2_F64
+               ? leapfrog_t<double>(e, d_q, d_p, d_var, epsilon, n_steps, d_q_out, d_p_out, d_energy_out, glm_path, (cudaStream_t)stream)
+               : leapfrog_t<float>(e, d_q, d_p, d_var, epsilon, n_steps, d_q_out, d_p_out, d_energy_out, glm_path, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- stepwise lock-step API
@@ -602,9 +699,8 @@ static int step_advance_t(b2_engine* e, const double* d_packed, int prior_copies
 }
 
 extern "C" int b2_step_begin(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* trace, void* stream) {
-    if (!e || !o) { b2_set_error("b2_step_begin: null argument"); return -1; }
-    if (!e->state_set) { b2_set_error("b2_step_begin: call b2_set_state first"); return -2; }
-    if (o->n_iters <= 0) { b2_set_error("b2_step_begin: n_iters must be > 0"); return -3; }
+    const int rc0 = check_run_args("b2_step_begin", e, o);
+    if (rc0) return rc0;
     B2_CUDA_OK(cudaSetDevice(e->device));
     e->step_opts = *o;
     memset(&e->step_trace, 0, sizeof(e->step_trace));
@@ -638,6 +734,11 @@ extern "C" int b2_step_likelihood(b2_engine* e, double* d_packed, void* stream) 
 extern "C" int b2_step_advance(b2_engine* e, const double* d_packed, int32_t prior_copies, void* stream) {
     if (!e || !d_packed || !e->stepping) { b2_set_error("b2_step_advance: call b2_step_begin first"); return -1; }
     if (prior_copies < 1) { b2_set_error("b2_step_advance: prior_copies must be >= 1"); return -2; }
+    if (prior_copies > 1 && e->md.family != B2_FAMILY_GLM_LOGIT) {
+        // only the GLM family knows how to take the surplus prior copies back out of a sum over row shards
+        b2_set_error("b2_step_advance: observation sharding (prior_copies > 1) is implemented for B2_GLM_LOGIT only");
+        return -3;
+    }
     B2_CUDA_OK(cudaSetDevice(e->device));
     return e->dtype == B2_F64 ? step_advance_t<double>(e, d_packed, prior_copies, (cudaStream_t)stream)
                               : step_advance_t<float>(e, d_packed, prior_copies, (cudaStream_t)stream);

@@ -65,11 +65,13 @@ void b2_glm_tcw_release(b2_engine* e);
 int b2_glm_tcw_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
                       const B2ChainState* st, int n, double* logp, cudaStream_t stream);
 void b2_glm_tc_release(b2_engine* e);
-// fused lock-step pieces of the tensor-core path: split/swizzle the pending positions, run the
-// likelihood, then {reduce slab partials, advance the chain state machine, re-split} in one kernel
+// lock-step pieces of the tensor-core path: slot maps at the start of a run, then one call per leapfrog
 int b2_glm_tc_pack(b2_engine* e, const float* qA, const float* qB, int ld, const B2ChainState* st, int n, cudaStream_t s);
-int b2_glm_tc_main(b2_engine* e, cudaStream_t s);
-int b2_glm_tc_post(b2_engine* e, const void* view_f32, cudaStream_t s);
+// one leapfrog of every live chain: fused schedule = 2 launches {likelihood(half h) + state machine(other half)},
+// two-kernel schedule (B2_TC_FUSED=0) = likelihood + state-machine kernel; `mid` (optional) is recorded between
+// the likelihood and the stand-alone state-machine kernel (after both launches in the fused schedule)
+int b2_glm_tc_step(b2_engine* e, const void* view_f32, cudaStream_t s, cudaEvent_t mid);
+bool b2_glm_tc_is_fused(const b2_engine* e);
 template <typename T>
 int b2_hier_launch(b2_engine* e, const T* qA, const T* qB, T* gA, T* gB, int ld,
                    const B2ChainState* st, int n_points, double* logp, cudaStream_t stream);

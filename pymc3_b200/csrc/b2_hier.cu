@@ -44,6 +44,52 @@ __global__ void k_hier_compact(const B2ChainState* st, int n_chains, int* cnt, i
     chain_of_slot[atomicAdd(cnt, 1)] = c;
 }
 
+// Per-thread running sums of one (chain, group) segment: S0 = sum r, S1 = sum r f, SS = sum r^2.
+// fp64 check build: plain double.  fp32 production build: the FP32 pipe is the bound of this kernel (5 flops per
+// (chain, observation)), so the inner loop uses Blackwell's packed fp32 math (FADD2 / FFMA2: two
+// observations per instruction, 2.5 issue slots per pair instead of 5) into four independent lanes per sum, and
+// the lanes are folded into DOUBLE totals at the end of every staged tile (<= HT_TILE rows, <= 512 addends per
+// lane) and at every group end -- a slab of 27 k rows (C3) is therefore never summed in fp32 end to end.
+template <typename T> struct HierAcc;
+template <> struct HierAcc<double> {
+    double s0, s1, ss;
+    __device__ __forceinline__ void clear() { s0 = 0.0; s1 = 0.0; ss = 0.0; }
+    __device__ __forceinline__ void set_group(double, double) {}
+    __device__ __forceinline__ void one(double A, double B, float y, float f) {
+        const double r = (double)y - (A + B * (double)f);
+        s0 += r; s1 += r * (double)f; ss += r * r;
+    }
+    __device__ __forceinline__ void four(double A, double B, const float4& y4, const float4& f4) {
+        one(A, B, y4.x, f4.x); one(A, B, y4.y, f4.y); one(A, B, y4.z, f4.z); one(A, B, y4.w, f4.w);
+    }
+    __device__ __forceinline__ void fold(double& d0, double& d1, double& dss) { d0 += s0; d1 += s1; dss += ss; clear(); }
+};
+template <> struct HierAcc<float> {
+    float2 a0, a1, a2, b0, b1, b2;            // lanes {x, y} of pair a (observations 0,1) and pair b (2,3)
+    float2 nA, nB;                            // (-A, -A), (-B, -B) of the current group
+    __device__ __forceinline__ void clear() {
+        a0 = a1 = a2 = b0 = b1 = b2 = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void set_group(float A, float B) { nA = make_float2(-A, -A); nB = make_float2(-B, -B); }
+    __device__ __forceinline__ void one(float A, float B, float y, float f) {
+        const float r = y - (A + B * f);
+        a0.x += r; a1.x = fmaf(r, f, a1.x); a2.x = fmaf(r, r, a2.x);
+    }
+    __device__ __forceinline__ void four(float, float, const float4& y4, const float4& f4) {
+        const float2 fa = make_float2(f4.x, f4.y), fb = make_float2(f4.z, f4.w);
+        const float2 ra = __ffma2_rn(nB, fa, __fadd2_rn(make_float2(y4.x, y4.y), nA));     // r = (y - A) - B f
+        const float2 rb = __ffma2_rn(nB, fb, __fadd2_rn(make_float2(y4.z, y4.w), nA));
+        a0 = __fadd2_rn(a0, ra); a1 = __ffma2_rn(ra, fa, a1); a2 = __ffma2_rn(ra, ra, a2);
+        b0 = __fadd2_rn(b0, rb); b1 = __ffma2_rn(rb, fb, b1); b2 = __ffma2_rn(rb, rb, b2);
+    }
+    __device__ __forceinline__ void fold(double& d0, double& d1, double& dss) {
+        d0 += (double)((a0.x + a0.y) + (b0.x + b0.y));
+        d1 += (double)((a1.x + a1.y) + (b1.x + b1.y));
+        dss += (double)((a2.x + a2.y) + (b2.x + b2.y));
+        clear();
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(HT_CHAINS)
 k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, const int* __restrict__ grp_off,
@@ -77,7 +123,10 @@ k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, c
     int g = s_g0;
     int g_end = grp_off[g + 1];
     T A = mu_a + sa * q[4 + g], B = mu_b + sb * q[4 + NG + g];
-    T s0 = (T)0, s1 = (T)0, ss = (T)0;
+    HierAcc<T> acc;
+    acc.clear();
+    acc.set_group(A, B);
+    double d0 = 0.0, d1 = 0.0, dss = 0.0;             // this group's S0, S1 so far; the slab's SS
     bool dirty = false;                                // rows accumulated since the last flush (block-uniform)
     T* pbase = part + (size_t)split * (2 * NG + 1) * n_chains;
     for (int t0 = row_begin; t0 < row_end; t0 += HT_TILE) {
@@ -91,37 +140,23 @@ k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, c
             if (i < stop) dirty = true;
             // scalar head up to a 4-aligned index, then 4 observations per shared-memory transaction
             // (one LDS.128 of y + one LDS.128 of the covariate, both broadcast to the warp)
-            for (; i < stop && (i & 3); ++i) {
-                const T f = (T)fs[i];
-                const T r = (T)ys[i] - (A + B * f);
-                s0 += r; s1 += r * f; ss += r * r;
-            }
-            for (; i + 4 <= stop; i += 4) {
-                const float4 y4 = *reinterpret_cast<const float4*>(ys + i);
-                const float4 f4 = *reinterpret_cast<const float4*>(fs + i);
-                const T yv[4] = {(T)y4.x, (T)y4.y, (T)y4.z, (T)y4.w};
-                const T fv[4] = {(T)f4.x, (T)f4.y, (T)f4.z, (T)f4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const T r = yv[k] - (A + B * fv[k]);
-                    s0 += r; s1 += r * fv[k]; ss += r * r;
-                }
-            }
-            for (; i < stop; ++i) {
-                const T f = (T)fs[i];
-                const T r = (T)ys[i] - (A + B * f);
-                s0 += r; s1 += r * f; ss += r * r;
-            }
+            for (; i < stop && (i & 3); ++i) acc.one(A, B, ys[i], fs[i]);
+#pragma unroll 2
+            for (; i + 4 <= stop; i += 4)
+                acc.four(A, B, *reinterpret_cast<const float4*>(ys + i), *reinterpret_cast<const float4*>(fs + i));
+            for (; i < stop; ++i) acc.one(A, B, ys[i], fs[i]);
+            acc.fold(d0, d1, dss);                      // end of this (tile, group) segment: lanes -> double totals
             if (t0 + i == g_end) {                      // group complete: flush and move on
                 if (live && dirty) {
-                    pbase[(size_t)g * n_chains + slot] = s0;
-                    pbase[(size_t)(NG + g) * n_chains + slot] = s1;
+                    pbase[(size_t)g * n_chains + slot] = (T)d0;
+                    pbase[(size_t)(NG + g) * n_chains + slot] = (T)d1;
                 }
-                s0 = (T)0; s1 = (T)0; dirty = false;
+                d0 = 0.0; d1 = 0.0; dirty = false;
                 ++g;
                 if (g < NG) {
                     g_end = grp_off[g + 1];
                     A = mu_a + sa * q[4 + g]; B = mu_b + sb * q[4 + NG + g];
+                    acc.set_group(A, B);
                 } else {
                     g_end = 0x7fffffff;
                 }
@@ -130,10 +165,10 @@ k_hier_slab(const float* __restrict__ y, const unsigned char* __restrict__ fl, c
     }
     if (live) {
         if (dirty && g < NG) {                         // group cut by the slab boundary
-            pbase[(size_t)g * n_chains + slot] = s0;
-            pbase[(size_t)(NG + g) * n_chains + slot] = s1;
+            pbase[(size_t)g * n_chains + slot] = (T)d0;
+            pbase[(size_t)(NG + g) * n_chains + slot] = (T)d1;
         }
-        pbase[(size_t)(2 * NG) * n_chains + slot] = ss;
+        pbase[(size_t)(2 * NG) * n_chains + slot] = (T)dss;
     }
 }
 

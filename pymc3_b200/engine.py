@@ -91,6 +91,25 @@ class Engine:
                                            int(glm_path), self._stream()), self.lib)
         return logp, grad
 
+    # -- CpuLeapfrogIntegrator.compute_state + n x .step (integration.py:39-109), all chains at once
+    def leapfrog(self, q, p, var, epsilon, n_steps, glm_path=_capi.B2_GLM_AUTO):
+        """q, p: [n_chains, D]; var: [D] diagonal of M^-1 -> (q', p', energy [n_chains]) device tensors after
+        `n_steps` leapfrog steps of size `epsilon` (negative = backwards).  Overwrites the sampler state."""
+        torch = self.torch
+        qd = torch.as_tensor(q, device=self.dev).to(self.t_dtype).contiguous()
+        pd = torch.as_tensor(p, device=self.dev).to(self.t_dtype).contiguous()
+        if qd.shape != (self.n_chains, self.D) or pd.shape != qd.shape:
+            raise ValueError("q and p must have shape (%d, %d)" % (self.n_chains, self.D))
+        vd = torch.as_tensor(np.ascontiguousarray(var, dtype="f8"), device=self.dev)
+        if vd.numel() != self.D:
+            raise ValueError("var must have %d elements" % self.D)
+        q_out, p_out = torch.empty_like(qd), torch.empty_like(pd)
+        energy = torch.empty(self.n_chains, dtype=torch.float64, device=self.dev)
+        _capi.check(self.lib.b2_leapfrog(self.handle, qd.data_ptr(), pd.data_ptr(), vd.data_ptr(), float(epsilon),
+                                         int(n_steps), q_out.data_ptr(), p_out.data_ptr(), energy.data_ptr(),
+                                         int(glm_path), self._stream()), self.lib)
+        return q_out, p_out, energy
+
     # -- sampling.py:410-413, 883-884, 1915-1929 + base_hmc.py:93-103
     def set_state(self, q0, seeds, step_size0, mass_mean, mass_var, mass_weight, adaptation_window=101):
         torch = self.torch

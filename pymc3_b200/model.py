@@ -103,9 +103,16 @@ class Model:
     def unobserved_RVs(self):          # model.py:954-957: free (transformed) + deterministics
         return self.free_RVs + self.deterministics
 
+    def _test_values(self):
+        """free-variable name -> default test value where it is not 0 (the reference takes each distribution's
+        first available default of ('median', 'mean', 'mode'), distribution.py:208, through its transform:
+        HalfCauchy -> log(beta) continuous.py:2401-2402, Exponential -> log(log 2 / lam) :1519-1521)."""
+        return {}
+
     @property
     def test_point(self):
-        return {n: np.zeros(s) for n, s in self.free}
+        tv = self._test_values()
+        return {n: np.full(s, float(tv.get(n, 0.0))) for n, s in self.free}
 
     def dict_to_array(self, point):
         od = self.ordering()
@@ -230,6 +237,9 @@ class EightSchoolsNCP(Model):
         self.mu_sd, self.tau_beta = float(mu_sd), float(tau_beta)
         self.free = (("eta", (self.J,)), ("mu", ()), ("tau_log__", ()))
 
+    def _test_values(self):
+        return {"tau_log__": np.log(self.tau_beta)}
+
     def _describe(self, upload):
         d = _capi.ModelDesc(family=self.family, D=self.J + 2, N=self.J, G=0)
         d.d_aux0 = upload(self.y, "f8")
@@ -290,6 +300,10 @@ class HierLinearNCP(Model):
         self.free = (("mu_a", ()), ("sigma_a_log__", ()), ("mu_b", ()), ("sigma_b_log__", ()),
                      ("a", (G,)), ("b", (G,)), ("eps_log__", ()))
 
+    def _test_values(self):
+        v = np.log(self.hc_beta)
+        return {"sigma_a_log__": v, "sigma_b_log__": v, "eps_log__": v}
+
     def _describe(self, upload):
         d = _capi.ModelDesc(family=self.family, D=2 * self.G + 5, N=self.N, G=self.G)
         d.d_y = upload(self.y, "f4")
@@ -312,6 +326,9 @@ class StochVol(Model):
         self.T = len(self.returns)
         self.step_lam, self.nu_lam = float(step_lam), float(nu_lam)
         self.free = (("step_size_log__", ()), ("volatility", (self.T,)), ("nu_log__", ()))
+
+    def _test_values(self):
+        return {"step_size_log__": np.log(np.log(2.0) / self.step_lam), "nu_log__": np.log(np.log(2.0) / self.nu_lam)}
 
     def _describe(self, upload):
         d = _capi.ModelDesc(family=self.family, D=self.T + 2, N=self.T, G=0)

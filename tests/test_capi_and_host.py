@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert set(names) == set(_capi.EXPORTS)
-    assert _capi.load_library().b2_abi_version() == 2
+    assert _capi.load_library().b2_abi_version() == _capi.ABI_VERSION == 3
 
 
 def test_ctypes_structs_match_header_layout():

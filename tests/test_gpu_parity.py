@@ -115,7 +115,7 @@ def test_glm_chain_batched_paths(dtype, tol, path):
     eng.close()
 
 
-@pytest.mark.parametrize("dtype,tol", [("float64", 1e-6), ("float32", 2e-4)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-6), ("float32", 1e-4)])
 def test_hier_chain_batched_kernel(dtype, tol):
     from oracle import densities as od
     from pymc3_b200 import model as pm
