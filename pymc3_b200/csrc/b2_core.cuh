@@ -28,6 +28,9 @@
 #include "b2_philox.cuh"
 
 #define B2_MAX_LEVELS 12          // stack buffers; max_treedepth <= 12
+#ifndef B2_WELFORD_WIDTH
+#define B2_WELFORD_WIDTH 4        // components per pass of the mass-matrix update (b2_glm_tc.cu builds with 2: register budget)
+#endif
 
 enum { B2_PHASE_INIT = 0, B2_PHASE_TREE = 1, B2_PHASE_HMC = 2, B2_PHASE_DONE = 3, B2_PHASE_FAILED = 4,
        B2_PHASE_RESUME = 5 };   // RESUME: a finished chain asked to continue (next b2_sample_run call)
@@ -433,22 +436,23 @@ B2_HD int b2_end_transition(const G& g, const B2View<T>& w, int c, B2ChainState&
         double* b2 = w.wv_m2 + ((size_t)b * w.C + c) * w.Dp;
         const double nf = s.wv_count[f] + 1.0, nb = s.wv_count[b] + 1.0;
         const bool swap = (s.n_seen > 0) && (s.n_seen % s.window == 0);
-        // four components per pass, loads first and stores last: 16 loads in flight and 12 independent fp64
+        // WW (four) components per pass, loads first and stores last: 16 loads in flight and 12 independent fp64
         // divisions instead of one load round trip and three dependent divisions per component (a chain that
         // ends its transition is the critical path of a lock-step launch)
-        for (int i0 = g.lane(); i0 < w.D; i0 += 4 * G::NT) {
-            double x[4], mf[4], rf[4], mb[4], rb[4];
+        constexpr int WW = B2_WELFORD_WIDTH;
+        for (int i0 = g.lane(); i0 < w.D; i0 += WW * G::NT) {
+            double x[WW], mf[WW], rf[WW], mb[WW], rb[WW];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < WW; ++u) {
                 const int i = i0 + u * G::NT;
                 const bool ok = i < w.D;
                 x[u] = ok ? (double)pq[i] : 0.0;
                 mf[u] = ok ? fm[i] : 0.0; rf[u] = ok ? f2[i] : 0.0;
                 mb[u] = ok ? bm[i] : 0.0; rb[u] = ok ? b2[i] : 0.0;
             }
-            T vnew[4];
+            T vnew[WW];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < WW; ++u) {
                 double od = x[u] - mf[u];
                 mf[u] = mf[u] + od / nf;
                 rf[u] = rf[u] + od * (x[u] - mf[u]);
@@ -458,7 +462,7 @@ B2_HD int b2_end_transition(const G& g, const B2View<T>& w, int c, B2ChainState&
                 rb[u] = rb[u] + od * (x[u] - mb[u]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < WW; ++u) {
                 const int i = i0 + u * G::NT;
                 if (i < w.D) {
                     var[i] = vnew[u];

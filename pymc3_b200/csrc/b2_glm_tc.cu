@@ -40,6 +40,7 @@
 #include <cuda_bf16.h>
 #include <cstring>
 #include <cstdlib>
+#define B2_WELFORD_WIDTH 2            // the state-machine warps of the fused launch live on 136 registers
 #include "b2_engine.cuh"
 #include "b2_tc_ptx.cuh"
 
@@ -71,6 +72,7 @@ struct TcWorkspace {
     int first, count;        // the chains this workspace covers: [first, first + count)
     int post_levels;         // merge levels whose stack buffers the state-machine warps stage in shared memory
     int* err;                // device watchdog flag
+    long long* role_clk;     // optional (B2_TC_ROLE_CLOCKS=1): {sum, count, max} cycles of the state-machine warps, then of the likelihood CTAs
     // per launch: where every chain's pending position lives
     const float* qA; const float* qB; int ld; const B2ChainState* st; int n_chains; int K1;
     // active-chain compaction: chains that still need a gradient are packed into dense 128-row tiles, so a
@@ -157,13 +159,14 @@ __device__ __forceinline__ double tc_finalize_chain(const TcWorkspace& ws, const
     const float4* gp = reinterpret_cast<const float4*>(ws.gpart + (size_t)slot * TC_KP) + lane;
     const size_t stride4 = (size_t)gm.stride * TC_KP / 4;
     // all slab partials of this lane in flight at once (one L2 round trip), then a fixed-order sum
-    for (int sp0 = 0; sp0 < gm.sp; sp0 += 24) {
-        float4 v[24];
+    // (12 per round: 48 registers; 24 at once pushed the state-machine warps of the fused launch past their budget)
+    for (int sp0 = 0; sp0 < gm.sp; sp0 += 12) {
+        float4 v[12];
 #pragma unroll
-        for (int j = 0; j < 24; ++j)
+        for (int j = 0; j < 12; ++j)
             v[j] = (sp0 + j < gm.sp) ? __ldcg(gp + (size_t)(sp0 + j) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 24; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        for (int j = 0; j < 12; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
     }
     const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
     double prior = 0.0;
@@ -202,24 +205,28 @@ __device__ __forceinline__ void tc_post_chain(const TcWorkspace& ws, B2View<floa
                                               float* hot, double* lvh, float* stk) {
     B2WarpGroup g;
     const long long t_start = w.dbg ? clock64() : 0;
-    // Everything this warp needs from global memory is requested before anything is stored to shared memory
-    // (the loads go through generic pointers, so the compiler keeps them behind earlier shared stores):
-    // one round trip for the chain state, its 11 hot vector slots, the level scalars and the slot maps.
+    // The chain's 11 hot vector slots go global -> shared with cp.async (no register staging: the state-machine
+    // warps of the fused launch run on a fixed register budget), in flight together with the level scalars, the
+    // chain state and -- second group -- the stack buffers of the pending merges.
     const int lane0 = threadIdx.x & 31;
-    float4 tmp[B2_V_STACK0];
+    if (4 * lane0 < w.Dp) {
 #pragma unroll
-    for (int slot = 0; slot < B2_V_STACK0; ++slot)
-        tmp[slot] = (4 * lane0 < w.Dp) ? *reinterpret_cast<const float4*>(w.Vglobal(slot, c) + 4 * lane0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int slot = 0; slot < B2_V_STACK0; ++slot) {
+            const uint32_t dst = smem_u32(hot + slot * w.Dp + 4 * lane0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(w.Vglobal(slot, c) + 4 * lane0) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const double* lv_src = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
     const double lv_a0 = lv_src[lane0];
     const double lv_a1 = (lane0 + 32 < 4 * B2_MAX_LEVELS) ? lv_src[lane0 + 32] : 0.0;
     const int my_slot = ws.slot_of_chain[c];
     const TcGeom gm = tc_geom(ws);
     B2ChainState s = w.st[c];
-    if (!b2_needs_grad(s.phase)) return;               // warp-uniform: nothing of this chain was evaluated
-#pragma unroll
-    for (int slot = 0; slot < B2_V_STACK0; ++slot)
-        if (4 * lane0 < w.Dp) *reinterpret_cast<float4*>(hot + slot * w.Dp + 4 * lane0) = tmp[slot];
+    if (!b2_needs_grad(s.phase)) {                     // warp-uniform: nothing of this chain was evaluated
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        return;
+    }
     lvh[lane0] = lv_a0;
     if (lane0 + 32 < 4 * B2_MAX_LEVELS) lvh[lane0 + 32] = lv_a1;
     // Stack buffers the pending leaf will merge (one per trailing one-bit of its index, nuts.py:347-389 as a
@@ -248,6 +255,7 @@ __device__ __forceinline__ void tc_post_chain(const TcWorkspace& ws, B2View<floa
         if (n_staged == n_merge && n_merge > 0) wb_buf = b2_map_get(s.slot_map, n_merge - 1);   // the merged sub-tree ends up here
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");            // the hot slots have landed; the stack buffers may not have
     __syncwarp();
     w.hot = hot;
     w.lv_hot = lvh;
@@ -419,9 +427,16 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (FUSED && warp >= TC_THREADS / 32) {
         // ===== state machine of the other half (its likelihood ran in the previous launch) =====
+        const long long tp0 = clock64();
         if (wsp.count > 0)
             tc_post_role(wsp, wview, wsp.K1, prior_tau, smem + (TC_MAIN_SMEM(STAGES) - 1024), warp - TC_THREADS / 32,
                          TC_POST_WARPS, blockIdx.x, gridDim.x);
+        if (ws.role_clk && lane == 0 && wsp.count > 0 && blockIdx.x * TC_POST_WARPS + warp - TC_THREADS / 32 < wsp.count) {
+            const unsigned long long dt = (unsigned long long)(clock64() - tp0);
+            atomicAdd((unsigned long long*)ws.role_clk + 0, dt);
+            atomicAdd((unsigned long long*)ws.role_clk + 1, 1ull);
+            atomicMax((unsigned long long*)ws.role_clk + 2, dt);
+        }
         return;
     }
     if (ws.count == 0) return;
@@ -433,106 +448,127 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
     const int t_end = min(ws.n_tiles, t_begin + gm.tps);
     const int T = t_end - t_begin;                 // >= 1: gm.sp counts only slabs that own rows
 
-    if (warp == 1 && lane == 0) {
-        mbar_init(q_full, TC_EPI_WARPS);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TC_EPI_WARPS / 2); mbar_init(p_full + i, TC_EPI_WARPS / 2); mbar_init(p_empty + i, 1); }
-        mbar_init(g_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    tc_main_sync();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== producer: Q tile once, then the X tile ring =====
-        if (lane == 0) {
-            for (int t = 0; t < T; ++t) {
-                const int s = t % STAGES;
-                if (t >= STAGES) mbar_wait(x_empty + s, ((t / STAGES) - 1) & 1, ws.err, 1);
-                const unsigned char* src = ws.xt + (size_t)(t_begin + t) * TC_STAGE_DATA;
-                mbar_expect_tx(x_full + s, TC_STAGE_DATA);
-                bulk_g2s(x_s + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, x_full + s);
-                bulk_g2s(y_s + s * TC_Y_BYTES, src + TC_STAGE_BYTES, TC_Y_BYTES, x_full + s);
-            }
+    // The two kinds of warps are kept in lexically separate branches (each with its own copy of the two CTA
+    // barriers) so that ptxas can give the control branch its own, smaller register budget.
+    if (warp < 4) {
+        // control warpgroup: 0 = bulk-copy producer, 1 = GEMM1 issuer, 2 = TMEM allocator, 3 = GEMM2 issuer
+        const long long tm0 = clock64();
+        if (warp == 1 && lane == 0) {
+            mbar_init(q_full, TC_EPI_WARPS);
+            for (int i = 0; i < STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TC_EPI_WARPS / 2); mbar_init(p_full + i, TC_EPI_WARPS / 2); mbar_init(p_empty + i, 1); }
+            mbar_init(g_full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-    } else if (warp == 1) {
-        // ===== GEMM1 issuer.  The whole warp runs the (warp-uniform) loop so descriptors and TMEM
-        // addresses stay in uniform registers; only tcgen05.mma / tcgen05.commit are issued by one
-        // elected lane.  (Under `if (lane == 0)` ptxas wrapped every UTCHMMA in an R2UR + per-thread
-        // election loop: ~75 cycles of issue per MMA against 32-64 cycles of tensor work.)
-        // GEMM1 and GEMM2 have their own issuing warps (1 and 3): tcgen05.mma issue blocks on a shallow
-        // queue, so with a single issuer every barrier poll between the two GEMMs was tensor idle time
-        // (timeline r1: 2460 cycles of issuer time per tile for 1536 cycles of tensor work).
-        mbar_wait(q_full, 0, ws.err, 2);                           // epilogue warps have written Q into TMEM
+        if (warp == 2) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        tc_main_sync();
         tc_fence_after();
-        const int ks = (ws.K1 + 15) >> 4;                          // K steps that hold real features (7 of 8 at D+1 = 101)
-        for (int t = 0; t < T; ++t) {
-            const int s = t % STAGES, b = t & 1;
-            if (lane == 0) TC_STAMP(0, t);
-            mbar_wait(x_full + s, (t / STAGES) & 1, ws.err, 3);
-            if (t >= 2) mbar_wait(s_empty + b, ((t >> 1) - 1) & 1, ws.err, 4);
-            tc_fence_after();
-            const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
-            const uint32_t d = tmem + TC_COL_S + 64 * b;
-            if (elect_one()) {
-                uint32_t acc = 0;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {              // Qhi.Xhi, Qlo.Xhi, Qhi.Xlo
-                    const uint32_t qa = tmem + TC_COL_Q + (pass == 1 ? 64 : 0);
-                    const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
-#pragma unroll
-                    for (int j = 0; j < TC_KP / 16; ++j) {
-                        if (j >= ks) break;                            // all-zero padding columns: no tensor work spent on them
-                        const uint32_t koff = (j & 3) * 32;
-                        const uint64_t bd = make_desc(xa + (j >> 2) * (TC_OBS * 128) + koff, 16, 1024);
-                        mma_ts(d, qa + j * 8, bd, TC_IDESC_G1, acc);   // A from TMEM: no 4 KB smem read per MMA
-                        acc = 1;
-                    }
+        const uint32_t tmem = *tmem_slot;
+        if (warp == 0) {
+            // ===== producer: Q tile once, then the X tile ring =====
+            if (lane == 0) {
+                for (int t = 0; t < T; ++t) {
+                    const int s = t % STAGES;
+                    if (t >= STAGES) mbar_wait(x_empty + s, ((t / STAGES) - 1) & 1, ws.err, 1);
+                    const unsigned char* src = ws.xt + (size_t)(t_begin + t) * TC_STAGE_DATA;
+                    mbar_expect_tx(x_full + s, TC_STAGE_DATA);
+                    bulk_g2s(x_s + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, x_full + s);
+                    bulk_g2s(y_s + s * TC_Y_BYTES, src + TC_STAGE_BYTES, TC_Y_BYTES, x_full + s);
                 }
-                tc_commit(s_full + b);
-                TC_STAMP(1, t);
             }
-            __syncwarp();
-        }
-    } else if (warp == 3) {
-        // ===== GEMM2 issuer: G += R(u) . Xtile(u), three split passes; releases the X stage and the R buffer
-        // N = features rounded up to 16 (UMMA N granularity at M = 128): 112 instead of 128 at D+1 = 101
-        const uint32_t n2 = (uint32_t)((ws.K1 + 15) & ~15);
-        const uint32_t idesc_g2 = TC_IDESC_BASE | (1u << 16) | ((n2 >> 3) << 17) | ((TC_CHAINS >> 4) << 24);
-        for (int u = 0; u < T; ++u) {
-            const int s = u % STAGES, b = u & 1;
-            if (lane == 0) TC_STAMP(2, u);
-            mbar_wait(p_full + b, (u >> 1) & 1, ws.err, 5);
+        } else if (warp == 1) {
+            // ===== GEMM1 issuer.  The whole warp runs the (warp-uniform) loop so descriptors and TMEM
+            // addresses stay in uniform registers; only tcgen05.mma / tcgen05.commit are issued by one
+            // elected lane.  (Under `if (lane == 0)` ptxas wrapped every UTCHMMA in an R2UR + per-thread
+            // election loop: ~75 cycles of issue per MMA against 32-64 cycles of tensor work.)
+            // GEMM1 and GEMM2 have their own issuing warps (1 and 3): tcgen05.mma issue blocks on a shallow
+            // queue, so with a single issuer every barrier poll between the two GEMMs was tensor idle time
+            // (timeline r1: 2460 cycles of issuer time per tile for 1536 cycles of tensor work).
+            mbar_wait(q_full, 0, ws.err, 2);                           // epilogue warps have written Q into TMEM
             tc_fence_after();
-            const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
-            const uint32_t p_base = tmem + TC_COL_P + 64 * b;
-            const uint32_t d = tmem + TC_COL_G;
-            if (elect_one()) {
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {              // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
-                    const uint32_t pa = p_base + (pass == 1 ? 32 : 0);
-                    const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
-#pragma unroll
-                    for (int j = 0; j < TC_OBS / 16; ++j) {
-                        // MN-major B: 2 feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
-                        const uint64_t bd = make_desc(xa + j * 2048, TC_OBS * 128, 1024);
-                        mma_ts(d, pa + j * 8, bd, idesc_g2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+            const int ks = (ws.K1 + 15) >> 4;                          // K steps that hold real features (7 of 8 at D+1 = 101)
+            for (int t = 0; t < T; ++t) {
+                const int s = t % STAGES, b = t & 1;
+                if (lane == 0) TC_STAMP(0, t);
+                mbar_wait(x_full + s, (t / STAGES) & 1, ws.err, 3);
+                if (t >= 2) mbar_wait(s_empty + b, ((t >> 1) - 1) & 1, ws.err, 4);
+                tc_fence_after();
+                const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
+                const uint32_t d = tmem + TC_COL_S + 64 * b;
+                if (elect_one()) {
+                    uint32_t acc = 0;
+    #pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {              // Qhi.Xhi, Qlo.Xhi, Qhi.Xlo
+                        const uint32_t qa = tmem + TC_COL_Q + (pass == 1 ? 64 : 0);
+                        const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
+    #pragma unroll
+                        for (int j = 0; j < TC_KP / 16; ++j) {
+                            if (j >= ks) break;                            // all-zero padding columns: no tensor work spent on them
+                            const uint32_t koff = (j & 3) * 32;
+                            const uint64_t bd = make_desc(xa + (j >> 2) * (TC_OBS * 128) + koff, 16, 1024);
+                            mma_ts(d, qa + j * 8, bd, TC_IDESC_G1, acc);   // A from TMEM: no 4 KB smem read per MMA
+                            acc = 1;
+                        }
                     }
+                    tc_commit(s_full + b);
+                    TC_STAMP(1, t);
                 }
-                tc_commit(x_empty + s);
-                tc_commit(p_empty + b);
-                if (u == T - 1) tc_commit(g_full);
-                TC_STAMP(3, u);
+                __syncwarp();
             }
-            __syncwarp();
+        } else if (warp == 3) {
+            // ===== GEMM2 issuer: G += R(u) . Xtile(u), three split passes; releases the X stage and the R buffer
+            // N = features rounded up to 16 (UMMA N granularity at M = 128): 112 instead of 128 at D+1 = 101
+            const uint32_t n2 = (uint32_t)((ws.K1 + 15) & ~15);
+            const uint32_t idesc_g2 = TC_IDESC_BASE | (1u << 16) | ((n2 >> 3) << 17) | ((TC_CHAINS >> 4) << 24);
+            for (int u = 0; u < T; ++u) {
+                const int s = u % STAGES, b = u & 1;
+                if (lane == 0) TC_STAMP(2, u);
+                mbar_wait(p_full + b, (u >> 1) & 1, ws.err, 5);
+                tc_fence_after();
+                const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
+                const uint32_t p_base = tmem + TC_COL_P + 64 * b;
+                const uint32_t d = tmem + TC_COL_G;
+                if (elect_one()) {
+    #pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {              // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
+                        const uint32_t pa = p_base + (pass == 1 ? 32 : 0);
+                        const uint32_t xa = x_addr + (pass == 2 ? TC_XPART_BYTES : 0);
+    #pragma unroll
+                        for (int j = 0; j < TC_OBS / 16; ++j) {
+                            // MN-major B: 2 feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
+                            const uint64_t bd = make_desc(xa + j * 2048, TC_OBS * 128, 1024);
+                            mma_ts(d, pa + j * 8, bd, idesc_g2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(x_empty + s);
+                    tc_commit(p_empty + b);
+                    if (u == T - 1) tc_commit(g_full);
+                    TC_STAMP(3, u);
+                }
+                __syncwarp();
+            }
         }
-    } else if (warp >= 4) {
+        tc_fence_before();
+        tc_main_sync();
+        if (warp == 2) {
+            tc_fence_after();
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+            if (ws.role_clk && lane == 0) {
+                const unsigned long long dt = (unsigned long long)(clock64() - tm0);
+                atomicAdd((unsigned long long*)ws.role_clk + 3, dt);
+                atomicAdd((unsigned long long*)ws.role_clk + 4, 1ull);
+                atomicMax((unsigned long long*)ws.role_clk + 5, dt);
+            }
+        }
+    } else {
+        tc_fence_before();
+        tc_main_sync();                                            // barriers initialised, TMEM allocated
+        tc_fence_after();
+        const uint32_t tmem = *tmem_slot;
         // ===== epilogue warpgroups: thread == (chain row, 16-observation column group) =====
         const int wq = warp & 3;                                     // TMEM lane quarter this warp may touch
         const int cg = (warp - 4) >> 2;                              // column group 0..3
@@ -630,12 +666,8 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
         }
         // logp partial of this column group; the finalize kernel adds the TC_EPI_GROUPS partials
         ws.lpart[((size_t)split * TC_EPI_GROUPS + cg) * gm.stride + slot] = logp;
-    }
-    tc_fence_before();
-    tc_main_sync();
-    if (warp == 2) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+        tc_fence_before();
+        tc_main_sync();                                            // every TMEM read is done: warp 2 may free it
     }
 }
 
@@ -738,14 +770,20 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
         B2_CUDA_OK(cudaMalloc(&shared.dbg, (48 * TC_DBG_TILES + 4096 * 16) * sizeof(long long)));
         B2_CUDA_OK(cudaMemsetAsync(shared.dbg, 0, (48 * TC_DBG_TILES + 4096 * 16) * sizeof(long long), stream));
     }
+    if (getenv("B2_TC_ROLE_CLOCKS")) {
+        B2_CUDA_OK(cudaMalloc(&shared.role_clk, 8 * sizeof(long long)));
+        B2_CUDA_OK(cudaMemsetAsync(shared.role_clk, 0, 8 * sizeof(long long), stream));
+    }
     hs->fused = env_int("B2_TC_FUSED", 1) != 0 && !shared.dbg;      // the timeline tools read the two-kernel step
     hs->epi = env_int("B2_TC_EPI", 1) != 0 ? 1 : 0;
     // shared memory of the fused launch: X ring + the four state-machine warps (hot slots + staged merge levels);
     // prefer the deeper ring, stage as many merge levels as still fit
     hs->stages_fused = env_int("B2_TC_STAGES", 5) <= 4 ? 4 : 5;
-    hs->post_levels = TC_POST_STAGE_MAX;
+    hs->post_levels = env_int("B2_TC_POST_LEVELS", TC_POST_STAGE_MAX);
+    if (hs->post_levels > TC_POST_STAGE_MAX) hs->post_levels = TC_POST_STAGE_MAX;
+    const size_t smem_cap = (size_t)env_int("B2_TC_SMEM_CAP", TC_SMEM_LIMIT);
     for (;;) {
-        if (tc_fused_smem(hs, e->Dp) <= TC_SMEM_LIMIT) break;
+        if (tc_fused_smem(hs, e->Dp) <= smem_cap) break;
         if (hs->post_levels > 3) { hs->post_levels -= 1; continue; }
         if (hs->stages_fused == 5) { hs->stages_fused = 4; hs->post_levels = TC_POST_STAGE_MAX; continue; }
         hs->post_levels -= 1;
@@ -781,7 +819,7 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
 void b2_glm_tc_release(b2_engine* e) {
     if (!e->glm_tc) return;
     TcHostState* hs = (TcHostState*)e->glm_tc;
-    cudaFree(hs->full.dbg); cudaFree(hs->full.xt); cudaFree(hs->full.err);
+    cudaFree(hs->full.dbg); cudaFree(hs->full.xt); cudaFree(hs->full.err); cudaFree(hs->full.role_clk);
     tc_ws_free(hs->full); tc_ws_free(hs->half[0]); tc_ws_free(hs->half[1]);
     delete hs;
     e->glm_tc = nullptr;
@@ -894,6 +932,17 @@ extern "C" int b2_debug_tc_timeline(b2_engine* e, long long* host_out) {
     return 0;
 }
 
+// debugging aid (B2_TC_ROLE_CLOCKS=1): cycles the fused launches spent in their two roles since the engine was built:
+// host_out[0..2] = {sum, count, max} over state-machine warps that had a chain, [3..5] the same over likelihood CTAs
+extern "C" int b2_debug_tc_role_clocks(b2_engine* e, long long* host_out) {
+    if (!e || !e->glm_tc) return -1;
+    TcHostState* hs = (TcHostState*)e->glm_tc;
+    if (!hs->full.role_clk) return -2;
+    B2_CUDA_OK(cudaDeviceSynchronize());
+    B2_CUDA_OK(cudaMemcpy(host_out, hs->full.role_clk, 6 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // clock64 stamps of chain 0 inside k_glm_tc_post, one row of 16 per leapfrog (ring of 4096)
 extern "C" int b2_debug_post_timeline(b2_engine* e, long long* host_out) {
     if (!e || !e->glm_tc) return -1;
@@ -917,7 +966,9 @@ int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, 
     memset(&none, 0, sizeof(none));
     B2View<float> v;
     memset(&v, 0, sizeof(v));
-    if ((rc = tc_launch<false>(e, hs, w, none, v, stream))) return rc;
+    if (env_int("B2_TC_HOOK_FUSED", 0)) rc = tc_launch<true>(e, hs, w, none, v, stream);     // timing aid: the fused build, no state-machine work
+    else rc = tc_launch<false>(e, hs, w, none, v, stream);
+    if (rc) return rc;
     k_glm_tc_finalize<<<(n + 3) / 4, 128, 0, stream>>>(w, n, e->md.G + 1, e->md.hp[0], qA, qB, gA, gB, ld, st, logp);
     B2_CUDA_OK(cudaGetLastError());
     e->launches += 1;
