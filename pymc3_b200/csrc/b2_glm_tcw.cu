@@ -52,6 +52,9 @@ struct TwWorkspace {
     const float* qA; const float* qB; int ld; const B2ChainState* st; int n_chains; int K;
     int* counter;            // live chains of this launch
     int* chain_of_slot;
+    int* x_flags;            // [0] != 0: some X element has a non-zero bf16 low part (set by the tiling kernel)
+    int n_pass;              // 3 split passes, or 2 when X is bf16-representable (Xlo == 0: config C5's generator)
+    int flush_tiles;         // the gradient accumulator is drained into the fp32 partials every flush_tiles tiles
 };
 
 struct TwGeom { int n_act, nt, sp, tps, stride; };
@@ -69,9 +72,10 @@ __device__ __forceinline__ TwGeom tw_geom(const TwWorkspace& ws) {
 }
 
 __global__ void k_glm_tcw_prep_x(const float* __restrict__ X, const float* __restrict__ y, int N, int K,
-                                 unsigned char* __restrict__ xt) {
+                                 unsigned char* __restrict__ xt, int* __restrict__ x_flags) {
     const int tile = blockIdx.x;
     unsigned char* blob = xt + (size_t)tile * TW_STAGE_DATA;
+    bool any_lo = false;
     for (int idx = threadIdx.x; idx < TW_OBS * TW_KP; idx += blockDim.x) {
         const int r = idx / TW_KP, c = idx - r * TW_KP;
         const int row = tile * TW_OBS + r;
@@ -81,7 +85,9 @@ __global__ void k_glm_tcw_prep_x(const float* __restrict__ X, const float* __res
         const int off = (c >> 6) * (TW_OBS * 128) + tc_swz(r, c & 63);
         *reinterpret_cast<__nv_bfloat16*>(blob + off) = hi;
         *reinterpret_cast<__nv_bfloat16*>(blob + TW_XPART_BYTES + off) = lo;
+        any_lo = any_lo || (__bfloat162float(lo) != 0.f);
     }
+    if (__syncthreads_or(any_lo) && threadIdx.x == 0) atomicOr(x_flags, 1);
     for (int r = threadIdx.x; r < TW_OBS; r += blockDim.x) {
         const int row = tile * TW_OBS + r;
         reinterpret_cast<float*>(blob + 2 * TW_XPART_BYTES)[r] = row < N ? y[row] : -1.f;   // -1: padding row
@@ -96,17 +102,34 @@ __global__ void k_glm_tcw_compact(const B2ChainState* st, int n_chains, int* cnt
     chain_of_slot[atomicAdd(cnt, 1)] = c;
 }
 
-// GEMM1 of one tile for a compile-time number of live K steps: 3 split passes (Qhi.Xhi, Qlo.Xhi, Qhi.Xlo), fully
-// unrolled, one uniform add per MMA (descriptor low word = per-tile base + constant)
-template <int KS>
+// GEMM1 of one tile for a compile-time number of live K steps and split passes, fully unrolled, one uniform add per
+// MMA (descriptor low word = per-tile base + constant).  The tensor core adds into its fp32 accumulator with
+// truncation (each add loses up to one ulp of the RUNNING sum, towards zero -- measured: a relative bias of
+// ~6e-7 on eta at 21 adds, 0.03 nats on a logp of -7e4), so the small cross terms go first, while the
+// accumulator is still ~2^-8 of its final size, and only the Qhi.Xhi adds run at full magnitude.
+// NPASS = 3: Qlo.Xhi, Qhi.Xlo, Qhi.Xhi;  NPASS = 2 (X is bf16-representable, Xlo == 0): Qlo.Xhi, Qhi.Xhi.
+template <int KS, int NPASS>
 __device__ __forceinline__ void tw_issue_gemm1(uint32_t d, uint32_t tmem, uint32_t dlo, uint32_t dhi, uint32_t idesc) {
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t qa = tmem + TW_COL_Q + (pass == 1 ? 128 : 0);
+    for (int pi = 0; pi < NPASS; ++pi) {
+        const bool q_lo = (pi == 0);                           // A operand: Q low part in the first pass only
+        const bool x_lo = (NPASS == 3 && pi == 1);             // B operand: X low part in the middle pass of three
+        const uint32_t qa = tmem + TW_COL_Q + (q_lo ? 128 : 0);
 #pragma unroll
         for (int j = 0; j < KS; ++j)
-            mma_ts_split(d, qa + j * 8, dlo + (((pass == 2 ? TW_XPART_BYTES : 0) + (j >> 2) * (TW_OBS * 128) + (j & 3) * 32) >> 4),
-                         dhi, idesc, (pass > 0 || j > 0) ? 1u : 0u);
+            mma_ts_split(d, qa + j * 8, dlo + (((x_lo ? TW_XPART_BYTES : 0) + (j >> 2) * (TW_OBS * 128) + (j & 3) * 32) >> 4),
+                         dhi, idesc, (pi > 0 || j > 0) ? 1u : 0u);
+    }
+}
+
+template <int NPASS>
+__device__ __forceinline__ void tw_issue_gemm1_ks(int ks, uint32_t d, uint32_t tmem, uint32_t dlo, uint32_t dhi, uint32_t idesc) {
+    switch ((ks + 1) >> 1) {                             // 8..16 live K steps, rounded up to even (zero columns)
+        case 8: tw_issue_gemm1<16, NPASS>(d, tmem, dlo, dhi, idesc); break;
+        case 7: tw_issue_gemm1<14, NPASS>(d, tmem, dlo, dhi, idesc); break;
+        case 6: tw_issue_gemm1<12, NPASS>(d, tmem, dlo, dhi, idesc); break;
+        case 5: tw_issue_gemm1<10, NPASS>(d, tmem, dlo, dhi, idesc); break;
+        default: tw_issue_gemm1<8, NPASS>(d, tmem, dlo, dhi, idesc); break;
     }
 }
 
@@ -126,8 +149,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
     uint64_t* s_empty = s_full + 4;                // 4
     uint64_t* p_full = s_empty + 4;                // 4
     uint64_t* p_empty = p_full + 4;                // 4
-    uint64_t* g_full = p_empty + 4;                // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
+    uint64_t* g_full = p_empty + 4;                // 1: completes once per flush chunk (GEMM2 of the chunk's last tile)
+    uint64_t* g_empty = g_full + 1;                // 1: every epilogue warp has drained the chunk's G
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TwGeom gm = tw_geom(ws);
@@ -143,6 +167,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
         for (int i = 0; i < TW_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 4); mbar_init(p_full + i, 4); mbar_init(p_empty + i, 1); }
         mbar_init(g_full, 1);
+        mbar_init(g_empty, TW_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -182,13 +207,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             if (elect_one()) {
                 // descriptors: low word = per-tile base + compile-time offset, high word constant
                 const uint32_t dlo = tc_desc_lo(x_addr, 16), dhi = tc_desc_hi(1024);
-                switch ((ks + 1) >> 1) {                             // 8..16 live K steps, rounded up to even (zero columns)
-                    case 8: tw_issue_gemm1<16>(d, tmem, dlo, dhi, idesc_g1); break;
-                    case 7: tw_issue_gemm1<14>(d, tmem, dlo, dhi, idesc_g1); break;
-                    case 6: tw_issue_gemm1<12>(d, tmem, dlo, dhi, idesc_g1); break;
-                    case 5: tw_issue_gemm1<10>(d, tmem, dlo, dhi, idesc_g1); break;
-                    default: tw_issue_gemm1<8>(d, tmem, dlo, dhi, idesc_g1); break;
-                }
+                if (ws.n_pass == 2) tw_issue_gemm1_ks<2>(ks, d, tmem, dlo, dhi, idesc_g1);
+                else tw_issue_gemm1_ks<3>(ks, d, tmem, dlo, dhi, idesc_g1);
                 tc_commit(s_full + (t & 3));
             }
             __syncwarp();
@@ -199,9 +219,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
         kh = kh > 128 ? 128 : (kh < 1 ? 1 : kh);                 // K = 128: the second half is all padding, N = 16 of zeros
         const uint32_t n2 = (uint32_t)((kh + 15) & ~15);
         const uint32_t idesc_g2 = TC_IDESC_BASE | (1u << 16) | ((n2 >> 3) << 17) | ((TW_CHAINS >> 4) << 24);
+        // The gradient accumulator is drained every F tiles (see the epilogue): thousands of truncating adds into
+        // one fp32 accumulator biased the gradient by 2e-4 at 3 M rows (round 2 parity test at C5's shard size).
+        const int F = ws.flush_tiles;
+        const int np = ws.n_pass;
         for (int u = 0; u < T; ++u) {
             const int s = u % TW_STAGES, b = u & 1;
+            const bool chunk_first = (u % F) == 0, chunk_last = ((u + 1) % F) == 0 || u == T - 1;
             mbar_wait(p_full + (u & 3), (u >> 2) & 1, ws.err, 5);
+            if (chunk_first && u > 0) mbar_wait(g_empty, ((u / F) - 1) & 1, ws.err, 10);   // the previous chunk's G has been read out
             tc_fence_after();
             const uint32_t x_addr = smem_u32(x_s + s * TW_STAGE_BYTES) + half * 2 * (TW_OBS * 128);
             const uint32_t p_base = tmem + TW_COL_P + 32 * b;
@@ -210,16 +236,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
                 // MN-major B: 64-feature atoms LBO = 4096 B apart, 8-row groups SBO = 1024 B apart
                 const uint32_t dlo = tc_desc_lo(x_addr, TW_OBS * 128), dhi = tc_desc_hi(1024);
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {              // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo
+                for (int pass = 0; pass < 3; ++pass) {              // Rhi.Xhi, Rlo.Xhi, Rhi.Xlo (the last only if Xlo != 0)
+                    if (pass == 2 && np == 2) break;
                     const uint32_t pa = p_base + (pass == 1 ? 16 : 0);
 #pragma unroll
                     for (int j = 0; j < TW_OBS / 16; ++j)
                         mma_ts_split(d, pa + j * 8, dlo + (((pass == 2 ? TW_XPART_BYTES : 0) + j * 2048) >> 4), dhi, idesc_g2,
-                                     (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+                                     (!chunk_first || pass > 0 || j > 0) ? 1u : 0u);
                 }
                 tc_commit(x_empty + s);
                 tc_commit(p_empty + (u & 3));
-                if (u == T - 1) tc_commit(g_full);
+                if (chunk_last) tc_commit(g_full);
             }
             __syncwarp();
         }
@@ -261,7 +288,38 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             if (lane == 0) mbar_arrive(q_full);
         }
         float lp_sum = 0.f, lp_comp = 0.f, r_sum = 0.f, r_comp = 0.f;   // Kahan: no fp64 in the tile loop
+        // Chunked gradient accumulation: after GEMM2 of a chunk's last tile (g_full) every epilogue warp adds its
+        // 32 columns of G into the slab's fp32 partial in global memory (round-to-nearest adds; the same thread
+        // owns the same elements every time, so plain load-add-store) and releases the accumulator (g_empty).
+        const int F = ws.flush_tiles;
+        const int n_chunks = (T + F - 1) / F;
+        int k_drain = 0;                                             // next chunk this warp has to drain
+        float* gout = ws.gpart + ((size_t)split * gm.stride + slot) * TW_KP + 128 * half + 32 * cg;
+        auto drain = [&](int k) {
+            mbar_wait(g_full, k & 1, ws.err, 8);
+            tc_fence_after();
+            uint32_t g32[32];
+            TC_LD32(tmem + lane_addr + TW_COL_G + 32 * cg, g32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(g_empty);                     // G is in registers: the next chunk may start
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 a = make_float4(__uint_as_float(g32[4 * i]), __uint_as_float(g32[4 * i + 1]),
+                                       __uint_as_float(g32[4 * i + 2]), __uint_as_float(g32[4 * i + 3]));
+                if (k > 0) {
+                    const float4 o = reinterpret_cast<const float4*>(gout)[i];
+                    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                }
+                reinterpret_cast<float4*>(gout)[i] = a;
+            }
+        };
         for (int t = cg; t < T; t += TW_EPI_GROUPS) {
+            // Before touching a tile of a new chunk, drain the chunks that end before it.  (Draining AFTER the tile
+            // instead would deadlock: storing R of tile c+3 waits for GEMM2 of tile c+1, which waits for all
+            // sixteen warps to have drained the chunk that ended at c.)
+            while (k_drain < n_chunks - 1 && (k_drain + 1) * F - 1 < t) { drain(k_drain); ++k_drain; }
             const int s = t % TW_STAGES, b = t & 1;
             const float4* ys4 = reinterpret_cast<const float4*>(y_s + s * TW_Y_BYTES);
             mbar_wait(s_full + cg, (t >> 2) & 1, ws.err, 6);
@@ -328,20 +386,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             ky = rsum - r_comp; kt = r_sum + ky;
             r_comp = (kt - r_sum) - ky; r_sum = kt;
         }
-        // the slab's gradient tile: G[chain row][this half's 128 features] -> global partials
-        mbar_wait(g_full, 0, ws.err, 8);
-        tc_fence_after();
-        float* gout = ws.gpart + ((size_t)split * gm.stride + slot) * TW_KP + 128 * half + 32 * cg;
-        {
-            uint32_t g32[32];
-            TC_LD32(tmem + lane_addr + TW_COL_G + 32 * cg, g32);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(gout)[i] =
-                    make_float4(__uint_as_float(g32[4 * i]), __uint_as_float(g32[4 * i + 1]),
-                                __uint_as_float(g32[4 * i + 2]), __uint_as_float(g32[4 * i + 3]));
-        }
+        // what is left: at least the last chunk, G[chain row][this half's 128 features] -> global partials
+        while (k_drain < n_chunks) { drain(k_drain); ++k_drain; }
         if (half == 0) {
             const size_t o = ((size_t)split * TW_EPI_GROUPS + cg) * gm.stride + slot;
             ws.lpart[o] = (double)lp_sum - (double)lp_comp;
@@ -426,8 +472,17 @@ static int tw_setup(b2_engine* e, cudaStream_t stream) {
     B2_CUDA_OK(cudaMalloc(&w.rpart, slabs * TW_EPI_GROUPS * TW_CHAINS * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&w.err, TC_ERR_INTS * sizeof(int)));
     B2_CUDA_OK(cudaMemsetAsync(w.err, 0, TC_ERR_INTS * sizeof(int), stream));
-    k_glm_tcw_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt);
+    B2_CUDA_OK(cudaMalloc(&w.x_flags, 4 * sizeof(int)));
+    B2_CUDA_OK(cudaMemsetAsync(w.x_flags, 0, 4 * sizeof(int), stream));
+    k_glm_tcw_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt, w.x_flags);
     B2_CUDA_OK(cudaGetLastError());
+    int has_lo = 1;                                          // one-time: is the Q.Xlo / R.Xlo pass multiplying zeros?
+    B2_CUDA_OK(cudaMemcpyAsync(&has_lo, w.x_flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_OK(cudaStreamSynchronize(stream));
+    w.n_pass = has_lo ? 3 : 2;
+    if (getenv("B2_TCW_PASSES") && atoi(getenv("B2_TCW_PASSES")) == 3) w.n_pass = 3;
+    w.flush_tiles = getenv("B2_TCW_FLUSH") ? atoi(getenv("B2_TCW_FLUSH")) : 128;
+    if (w.flush_tiles < 8) w.flush_tiles = 8;
     B2_CUDA_OK(cudaFuncSetAttribute(k_glm_tcw_main, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES));
     e->launches += 1;
     e->glm_tcw = hs;
@@ -438,7 +493,7 @@ void b2_glm_tcw_release(b2_engine* e) {
     if (!e->glm_tcw) return;
     TwHostState* hs = (TwHostState*)e->glm_tcw;
     cudaFree(hs->ws.xt); cudaFree(hs->ws.counter); cudaFree(hs->ws.chain_of_slot); cudaFree(hs->ws.gpart);
-    cudaFree(hs->ws.lpart); cudaFree(hs->ws.rpart); cudaFree(hs->ws.err);
+    cudaFree(hs->ws.lpart); cudaFree(hs->ws.rpart); cudaFree(hs->ws.err); cudaFree(hs->ws.x_flags);
     delete hs;
     e->glm_tcw = nullptr;
 }

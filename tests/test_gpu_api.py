@@ -134,7 +134,7 @@ def test_divergences_are_reported():
         trace = pm.sample(200, tune=0, chains=2, step=step, random_seed=5, compute_convergence_checks=False)
     assert trace.get_sampler_stats("diverging").any()
     msgs = [w.message for w in trace.report._warnings]
-    assert any("divergence" in m.lower() for m in msgs)
+    assert any("diverg" in m.lower() for m in msgs)       # "N divergences" or "only diverging samples"
     assert not trace.report.ok
     with pytest.raises(ValueError):
         trace.report.raise_ok()
