@@ -4,16 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
 
 Metric (BASELINE.json): leapfrog gradient evaluations / second, whole job (all chains, all GPUs),
-with min bulk ESS / second reported beside it.  Workload (default, `c2`): Bernoulli-logit GLM
-N=100 000, D=100 (+intercept), 1024 chains per GPU, synthetic data of SURVEY 8(d).
+with min bulk ESS / second reported beside it.  Headline workload (config 2): Bernoulli-logit GLM
+N=100 000, D=100 (+intercept), 1024 chains per GPU, synthetic data of SURVEY 8(d).  With the default
+`--workload all` the line also carries `configs`: shortened but complete jobs (tune + draws, ESS,
+roofline, e2e) of config 1 (eight schools, with the CPU arm's ESS/s beside it), config 3 (radon NCP,
+N = 1 M, 4096 chains split over the GPUs), config 4 (stochastic volatility, 512 chains split over the
+GPUs), config 5 (logistic regression, rows sharded over the GPUs, all-reduce per leapfrog) and `c2s`
+(a reduced config 2 that the CPU arm can finish: the ESS/s ratio on the same job).
 
 A "step" is `--iters-per-step` (100) NUTS transitions of every chain, continuing one sampling job:
 the first half of the (W+K)*100 iterations tunes (dual averaging + diagonal mass adaptation), the
 second half draws.  With the defaults W=3, K=17 this is exactly tune=1000 / draws=1000.
 
   value  grad-evals/s over the K timed steps, data and state resident in HBM (CUDA events)
-  e2e    same metric for a second, identical job in which every step also copies the step's inputs
-         (X, y) host->device from pinned memory and reads the step's trace + stats back to the host
+  e2e    same metric for the same job run through the public API, pymc3_b200.sample(): model upload,
+         sampling, trace download (chunk by chunk, overlapped), MultiTrace construction
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md section 6
 
 `--impl reference` times the CPU implementation of the same path (the oracle port of the
@@ -205,52 +210,185 @@ def cpu_reference_run(wl, steps, warmup, budget_s, cores, iters_per_step=1):
 
 
 # ------------------------------------------------------------------------------- GPU arm
-def run_b200(args):
+class Ctx:
+    """rank / device / collectives of this process (one process per GPU)"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
+        self.dev = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.dev)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, seconds, counts):
+        """max over ranks of `seconds`, sum over ranks of `counts` (pymc3_b200/distributed.py)"""
+        from pymc3_b200 import distributed as b2d
+        return b2d.reduce_job_metrics(seconds, counts, device=self.dev)
+
+    def min_ess(self, ess_vec):
+        from pymc3_b200 import distributed as b2d
+        return b2d.combine_ess(ess_vec, device=self.dev)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def nuts_opts(args, exec_mode=0):
+    return dict(max_treedepth=10, early_max_treedepth=8, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75,
+                t0=10.0, adapt_step_size=1, adapt_mass=1, path_length=2.0, max_steps=1024, hmc_jitter=0,
+                exec_mode=exec_mode, glm_path={"auto": 0, "group": 1, "simt": 2, "tcgen05": 3}[args.glm_path])
+
+
+def device_ess(q_draws, model=None, max_cols=512):
+    """min-bulk-ESS input: rank-normalised split bulk ESS of every free scalar, computed where the trace lives
+    (pymc3_b200/stats_device.py, pinned to the NumPy estimator).  Bulk ESS is rank based, so the monotone
+    back-transforms (exp of the log-scale variables) have the same ESS as the free variables.
+    q_draws: [draws, C, D] device tensor -> (ess [K] numpy, note)"""
     import torch
-    import torch.distributed as dist
-    from pymc3_b200 import _capi, stats as b2stats
+    from pymc3_b200 import stats_device
+    Dq = q_draws.shape[2]
+    note = "every scalar of every free variable (= of every back-transformed one: bulk ESS is rank based)"
+    cols = None
+    if Dq > max_cols:
+        cols = np.unique(np.concatenate([np.arange(8), np.arange(Dq - 8, Dq), np.linspace(8, Dq - 9, 112).astype(int)]))
+        q_draws = q_draws[:, :, torch.as_tensor(cols, device=q_draws.device)]
+        note = "%d of %d free scalars (first/last 8 + 112 evenly spaced)" % (len(cols), Dq)
+    out = []
+    for lo in range(0, q_draws.shape[2], 32):                       # 32 columns at a time: bounded workspace
+        x = stats_device.from_trace(q_draws[:, :, lo:lo + 32])
+        out.append(stats_device.ess_bulk(x).cpu().numpy())
+    return np.concatenate(out), note
 
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
 
-    wl = make_workload(args.workload, args)
+def start_dicts(model, chains, first_chain):
+    """jittered start points as pm.sample takes them: test point + U(-1, 1) (sampling.py:1920-1926), keyed by
+    global chain id"""
+    tp = model.dict_to_array(model.test_point)
+    out = []
+    for c in range(chains):
+        q = tp + np.random.default_rng([7, first_chain + c]).uniform(-1, 1, size=len(tp))
+        out.append(model.array_to_dict(q))
+    return out
+
+
+def sample_config(ctx, args, wl, chains_total, tune, draws, split="strong", profile_chunks=0, chunk=100):
+    """One complete NUTS job through the PUBLIC API (pymc3_b200.sample) on this rank's share of the chains.
+    Returns the per-config result object (rank 0) -- value from the CUDA-event time of the sampling launches inside
+    the call, e2e from the wall clock around the whole call (model upload, sampling, trace download, MultiTrace)."""
+    import pymc3_b200 as pm
+    from pymc3_b200 import distributed as b2d
+    torch = ctx.torch
+    model = wl["model"]
+    if split == "strong":
+        lo, hi = b2d.shard_chains(chains_total, ctx.world, ctx.rank)
+    else:                                                     # weak: every rank runs chains_total chains of its own
+        lo, hi = ctx.rank * chains_total, (ctx.rank + 1) * chains_total
+    chains = hi - lo
+    starts = start_dicts(model, chains, lo)
+    seeds = [int(x) for x in chain_seeds(chains, lo)]
+    ctx.barrier()
+    t0 = time.perf_counter()
+    with model:
+        step = pm.NUTS(device=ctx.local_rank, dtype=args.dtype, glm_path=args.glm_path)
+        step._profile_last_chunks = profile_chunks
+        trace = pm.sample(draws, tune=tune, chains=chains, step=step, start=starts, random_seed=seeds, chunk=chunk,
+                          discard_tuned_samples=False, compute_convergence_checks=False, progressbar=False)
+    torch.cuda.synchronize(ctx.dev)
+    wall = time.perf_counter() - t0
+    ctx.barrier()
+    n_grad = step._last_n_grad
+    reports = step._last_reports
+    failed = sum(1 for r in reports if r.phase != 3)
+    # min bulk ESS over post-tune draws, from the host trace pushed back to the device in slabs (cheap next to the job)
+    ess_vec, ess_note = None, None
+    if draws >= 100:
+        names = model.free_RVs
+        cols = [np.stack(trace.get_values(n, burn=tune, combine=False)).reshape(chains, draws, -1) for n in names]
+        q = np.concatenate(cols, axis=2)                      # [C, draws, D]
+        qd = torch.as_tensor(np.ascontiguousarray(np.swapaxes(q, 0, 1)), device=ctx.dev)
+        ess_vec, ess_note = device_ess(qd)
+        del qd, q, cols
+    stats_tree = trace.get_sampler_stats("tree_size")
+    depth = trace.get_sampler_stats("depth")
+    secs, counts = ctx.reduce([step._last_device_seconds, wall], [n_grad, step._last_kernel_launches, failed, chains])
+    res = {"value": counts[0] / secs[0], "unit": "grad-evals/s", "chains_total": int(counts[3]), "chains_this_rank": chains,
+           "tune": tune, "draws": draws, "job_seconds_device": secs[0], "job_seconds_wall": secs[1],
+           "e2e": {"value": counts[0] / secs[1], "unit": "grad-evals/s",
+                   "through": "pymc3_b200.sample(): model upload, sampling, trace download into pinned staging, MultiTrace"},
+           "gpu_launches": int(counts[1]), "failed_chains": int(counts[2]),
+           "mean_tree_size": float(stats_tree.mean()), "mean_depth_post_tune": float(depth.reshape(chains, -1)[:, tune:].mean()),
+           "scaling": split}
+    if ess_vec is not None:
+        mn, _ = ctx.min_ess(ess_vec)
+        res["ess"] = {"min_bulk_ess": mn, "n_scalars": int(len(ess_vec)), "over": ess_note}
+        res["min_bulk_ess_per_sec"] = mn / secs[1]           # whole job incl. tuning, wall clock (benchmarks.py:163-169)
+    res["_profile"] = step._last_profile
+    del trace
+    return res
+
+
+def lockstep_roofline(prof, wl, peaks, bound):
+    """roofline object of a lock-step workload from the launches timed inside the job's last chunks"""
+    if not prof or not prof.get("like_n"):
+        return None
+    per_launch_s = prof["like_ms"] / 1e3 / prof["like_n"]
+    units = prof["n_grad"] / prof["like_n"]                  # chain-gradients one likelihood launch processed
+    out = {"kernel": "chain-batched likelihood (logp+dlogp, all live chains)", "launches_timed": int(prof["like_n"]),
+           "chain_grads_per_launch": units, "avg_launch_us": per_launch_s * 1e6,
+           "kernel_share_of_slice": prof["like_ms"] / 1e3 / prof["seconds"],
+           "advance_kernel_avg_us": prof["adv_ms"] * 1e3 / prof["like_n"],
+           "advance_share_of_slice": prof["adv_ms"] / 1e3 / prof["seconds"],
+           "timed_in": "the last chunks of the job, CUDA events around every launch (adds ~7 % to those chunks)",
+           "peak_source": peaks["source"], "traffic": None}
+    if bound == "tensor":
+        ach = wl["flops_per_chain_grad"] * units / per_launch_s / 1e12
+        out.update({"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"]})
+    else:
+        ach = wl["bytes_per_chain_grad"] * units / per_launch_s / 1e9
+        out.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]})
+        if wl.get("flops_per_chain_grad"):
+            # SURVEY 8d: once a tile of observations is shared by 128 chains the bound is FP32 issue, not HBM
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # nominal: SMs x FP32 lanes x 2 x max SM clock
+            fl = wl["flops_per_chain_grad"] * units / per_launch_s / 1e12
+            out.update({"fp32_achieved_tflops": fl, "fp32_peak_tflops_nominal": fp32_peak, "fp32_frac": fl / fp32_peak})
+    return out
+
+
+def run_c2_headline(ctx, args):
+    """Headline (BASELINE.json config 2): value from an engine-level job with everything resident in HBM, e2e from
+    the same job through pymc3_b200.sample, roofline from a short profiled slice that continues the first job."""
+    import torch
+    from pymc3_b200 import _capi
+    wl = make_workload("c2", args)
     model, chains = wl["model"], wl["chains"]          # chains per GPU (weak scaling)
-    first_chain = rank * chains
+    first_chain = ctx.rank * chains
     ndim = model.ndim
-    ips = args.iters_per_step
-    K, W = args.steps, args.warmup
+    ips, K, W = args.iters_per_step, args.steps, args.warmup
     total = (K + W) * ips
     tune = total // 2
-    opts = dict(max_treedepth=10, early_max_treedepth=8, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75,
-                t0=10.0, adapt_step_size=1, adapt_mass=1, path_length=2.0, max_steps=1024, hmc_jitter=0,
-                exec_mode=_capi.B2_EXEC_AUTO,
-                glm_path={"auto": 0, "group": 1, "simt": 2, "tcgen05": 3}[args.glm_path])
+    opts = nuts_opts(args)
     q0 = start_points(ndim, chains, first_chain)
     seeds = chain_seeds(chains, first_chain)
+    dev = ctx.dev
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def new_engine():
-        eng = model.engine(chains, dtype=args.dtype, device=local_rank)
-        eng.set_state(q0, seeds, 0.25 / ndim ** 0.25, np.zeros(ndim), np.ones(ndim), 10.0)
-        return eng
-
-    # ---- pass A: data and chain state resident in HBM
-    eng = new_engine()
+    eng = model.engine(chains, dtype=args.dtype, device=ctx.local_rank)
+    eng.set_state(q0, seeds, 0.25 / ndim ** 0.25, np.zeros(ndim), np.ones(ndim), 10.0)
     trace = eng.alloc_trace(_capi.B2_NUTS, total)          # the whole job's device trace, allocated up front
-    barrier()
+    ctx.barrier()
     tw0 = time.perf_counter()
-    ahead = args.run_ahead                 # lock-step runs: fast chains go on into the next step's rows (no-op otherwise)
+    ahead = args.run_ahead
 
     def grads(e):
         return sum(r.n_grad for r in e.reports())
@@ -259,11 +397,11 @@ def run_b200(args):
         eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=s * ips, run_ahead=ahead)
     torch.cuda.synchronize(dev)
     wall_warm = time.perf_counter() - tw0
-    clocks = ClockSampler(local_rank)
-    barrier()
-    if rank == 0 and not args.no_clocks:
+    clocks = ClockSampler(ctx.local_rank)
+    ctx.barrier()
+    if ctx.rank == 0 and not args.no_clocks:
         clocks.start()
-    eng.set_profiling(False)                 # per-launch events cost ~7 % of a lock-step step: separate pass P below
+    eng.set_profiling(False)
     launches0 = eng.kernel_launches()
     grads0 = grads(eng)                      # leapfrogs are counted when they are executed (engine counters)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -272,193 +410,198 @@ def run_b200(args):
     for s in range(K):
         eng.run(_capi.B2_NUTS, ips, tune, opts, out=trace, row0=(W + s) * ips, run_ahead=ahead)
     ev1.record()
-    barrier()
+    ctx.barrier()
     wall_timed = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
-    clock_info = clocks.stop() if rank == 0 else None
+    clock_info = clocks.stop() if ctx.rank == 0 else None
     launches = eng.kernel_launches() - launches0
     reports = eng.reports()
     leap_timed = sum(r.n_grad for r in reports) - grads0
     failed = sum(1 for r in reports if r.phase != _capi.PHASE_DONE)
-    eng.close()
 
-    tree = trace["tree_size"]                                           # [total, C]
-    leap_all = int(tree.sum().item())
-    t_vec = torch.tensor([dev_ms / 1e3, wall_timed, wall_warm], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([leap_timed, leap_all, launches, failed], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_vec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_timed = float(t_vec[0].item())
-    value = float(cnt[0].item()) / t_timed
-
-    # ---- min bulk ESS over every scalar of every free and back-transformed variable (post-tune draws)
-    ess_info = None
-    if not args.skip_ess and total - tune >= 100:
-        q = trace["q"][tune:]                                              # [draws, C, D]
-        ess_note = "every scalar of every free and back-transformed variable"
-        if q.shape[2] > 512:
-            # rank-normalised ESS of ~3000 scalars x 512k draws takes minutes on the host: the hyper-parameters
-            # (first and last 8 columns) plus 112 evenly spaced latent states; bulk ESS is rank based, so the
-            # elementwise monotone back-transforms do not change it
-            Dq = q.shape[2]
-            cols = np.unique(np.concatenate([np.arange(8), np.arange(Dq - 8, Dq),
-                                             np.linspace(8, Dq - 9, 112).astype(int)]))
-            qs = q[:, :, torch.as_tensor(cols, device=q.device)]
-            qs = qs.permute(1, 0, 2).contiguous().cpu().numpy().astype("f8")
-            ess_vec = np.ravel(b2stats.ess(qs))
-            ess_note = "%d of %d free scalars (first/last 8 + 112 evenly spaced)" % (len(cols), Dq)
-        else:
-            q = q.permute(1, 0, 2).contiguous().cpu().numpy().astype("f8")  # [C, draws, D]
-            vals = model.expand(q)
-            ess_vec = np.concatenate([np.ravel(b2stats.ess(v)) for v in vals.values()])
-        ess_t = torch.tensor(ess_vec, dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ess_t, op=dist.ReduceOp.SUM)                    # independent chain sets add
-        ess_info = {"min_bulk_ess": float(ess_t.min().item()), "n_scalars": int(ess_t.numel()), "over": ess_note}
-    del trace
-
-    # ---- pass P: the same job again with CUDA events around every likelihood / advance launch of the K timed
-    #      steps (kernel durations for the roofline; its own elapsed time is the denominator of the shares)
-    like_ms, like_n, adv_ms, prof_ms, leap_prof = 0.0, 0, 0.0, 0.0, 0
-    if not args.no_profile and rank == 0 and args.workload in ("c2", "c3"):     # the lock-step workloads
-        eng = new_engine()
-        ptrace = eng.alloc_trace(_capi.B2_NUTS, total)
-        for s in range(W):
-            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=s * ips, run_ahead=ahead)
-        torch.cuda.synchronize(dev)
+    # ---- profiled slice: the same chains go on for a few more (post-tuning) steps with CUDA events around every
+    #      likelihood / advance launch; the roofline's kernel duration and the chain-gradients per launch come from here
+    prof = None
+    if not args.no_profile and ctx.rank == 0:
+        P = 2
+        scratch = eng.alloc_trace(_capi.B2_NUTS, P * ips)
         eng.set_profiling(True)
         pg0 = grads(eng)
-        pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pv0.record()
-        for s in range(K):
-            eng.run(_capi.B2_NUTS, ips, tune, opts, out=ptrace, row0=(W + s) * ips, run_ahead=ahead)
-        pv1.record()
+        tp0 = time.perf_counter()
+        for s in range(P):
+            eng.run(_capi.B2_NUTS, ips, tune, opts, out=scratch, row0=s * ips, run_ahead=ahead)
         torch.cuda.synchronize(dev)
-        prof_ms = pv0.elapsed_time(pv1)
         like_ms, like_n = eng.profile()
-        adv_ms = eng.profile_advance()
-        leap_prof = grads(eng) - pg0
-        eng.close()
-        del ptrace
-
-    # ---- pass B: end to end -- every step uploads its inputs from pinned host memory and reads
-    #      its trace + stats back into pinned host memory (same seeds => same job)
-    eng = new_engine()
-    host_in = [t.cpu().pin_memory() for t in eng._keep]
-    h2d = sum(t.numel() * t.element_size() for t in host_in)
-    pinned, d2h = {}, 0
-    etrace = eng.alloc_trace(_capi.B2_NUTS, total)
-    for s in range(W):
-        eng.run(_capi.B2_NUTS, ips, tune, opts, out=etrace, row0=s * ips, run_ahead=ahead)
-    barrier()
-    eg0 = grads(eng)
-    e0 = time.perf_counter()
-    for s in range(K):
-        for src, dst in zip(host_in, eng._keep):
-            dst.copy_(src, non_blocking=True)
-        out = eng.run(_capi.B2_NUTS, ips, tune, opts, out=etrace, row0=(W + s) * ips, run_ahead=ahead)
-        for name, t in out.items():                    # this step's rows are complete for every chain
-            if name not in pinned:
-                pinned[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            pinned[name].copy_(t, non_blocking=True)
-        torch.cuda.synchronize(dev)
-    barrier()
-    e2e_s = time.perf_counter() - e0
-    leap_e2e = grads(eng) - eg0
-    del etrace
-    d2h = sum(t.numel() * t.element_size() for t in pinned.values())
+        prof = {"seconds": time.perf_counter() - tp0, "n_grad": grads(eng) - pg0, "like_ms": like_ms, "like_n": like_n,
+                "adv_ms": eng.profile_advance()}
+        del scratch
     eng.close()
-    e_vec = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    l_vec = torch.tensor([leap_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_vec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(l_vec, op=dist.ReduceOp.SUM)
-    e2e_value = float(l_vec.item()) / float(e_vec.item())
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    secs, cnt = ctx.reduce([dev_ms / 1e3, wall_timed, wall_warm], [leap_timed, launches, failed])
+    t_timed = secs[0]
+    value = cnt[0] / t_timed
+    ess_info = None
+    if not args.skip_ess and total - tune >= 100:
+        ess_vec, ess_note = device_ess(trace["q"][tune:])
+        mn, _ = ctx.min_ess(ess_vec)
+        ess_info = {"min_bulk_ess": mn, "n_scalars": int(len(ess_vec)), "over": ess_note}
+    del trace
+    torch.cuda.empty_cache()
+
+    # ---- e2e: the same job through the call a user makes
+    e2e = None
+    if not args.skip_e2e:
+        r = sample_config(ctx, args, wl, chains, tune, total - tune, split="weak", chunk=ips)
+        x_bytes = sum(t.numel() * t.element_size() for t in [torch.as_tensor(model.X), torch.as_tensor(model.y)])
+        d2h = (chains * ndim * 4 + chains * (7 * 8 + 2 * 4 + 2)) * ips          # one step's rows of q + 11 stats
+        e2e = {"value": r["e2e"]["value"], "unit": "grad-evals/s", "h2d_bytes_per_step": int(x_bytes // (K + W)),
+               "d2h_bytes_per_step": int(d2h), "job_seconds_wall": r["job_seconds_wall"],
+               "job_seconds_device": r["job_seconds_device"], "through": r["e2e"]["through"],
+               "note": "one pymc3_b200.sample() call for the whole job (tune + draws): X, y are uploaded once per call "
+                       "(h2d per step = that upload / steps), every chunk of %d transitions is copied to the host while "
+                       "the next one samples; convergence checks off (the bench computes ESS itself)" % ips}
+    if ctx.rank != 0:
+        return None
 
     peaks = measured_peaks()
-    roofline = None
-    traffic = None
+    roofline = lockstep_roofline(prof, wl, peaks, "tensor")
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if args.workload == "c2" and os.path.exists(tpath):        # one ncu --set full capture, per launch
+    if roofline is not None and os.path.exists(tpath):         # one ncu --set full capture, per launch (constant, not live)
         with open(tpath) as f:
-            traffic = json.load(f).get("k_glm_tc_main", {}).get("dram_bytes_per_launch")
-    if args.workload == "c4":
-        # persistent kernel: one launch per step, so the per-unit figure of SURVEY 8d (70 KB per chain-grad if the
-        # state streamed through HBM) is set against the whole-step rate
-        ach = wl["bytes_per_chain_grad"] * value / max(world, 1) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": None, "kernel": "k_persistent_block (whole NUTS transition loop, one launch per step)",
-                    "regime": "hot state (q, p, grad, p_sum, proposal, mass) is resident in shared memory, so the kernel is "
-                              "instruction-issue bound (ncu: issue slots 44 % busy, DRAM 27 GB/s), not HBM bound",
-                    "peak_source": peaks["source"]}
-    if like_n > 0 and wl["bound"]:
-        per_launch_s = like_ms / 1e3 / like_n
-        # units one launch processes = chains still inside a trajectory (the launch skips finished chains and,
-        # on the tensor-core path, compacts the live ones into dense tiles): counted, not assumed
-        units = leap_prof / like_n
-        if wl["bound"] == "tensor":
-            ach = wl["flops_per_chain_grad"] * units / per_launch_s / 1e12
-            roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tflops"], "traffic": traffic}
-        else:
-            ach = wl["bytes_per_chain_grad"] * units / per_launch_s / 1e9
-            roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": None}
-            if wl.get("flops_per_chain_grad"):
-                # once a tile of observations is shared by 128 chains the bound is FP32 issue, not HBM
-                fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # nominal: SMs x FP32 lanes x 2 x max SM clock
-                fl = wl["flops_per_chain_grad"] * units / per_launch_s / 1e12
-                roofline.update({"fp32_achieved_tflops": fl, "fp32_peak_tflops_nominal": fp32_peak, "fp32_frac": fl / fp32_peak})
-        roofline.update({"kernel": "chain-batched likelihood (logp+dlogp, all chains)", "launches_timed": int(like_n),
-                         "chain_grads_per_launch": units,
-                         "avg_launch_us": per_launch_s * 1e6, "kernel_share_of_step": like_ms / prof_ms,
-                         "advance_kernel_avg_us": adv_ms * 1e3 / like_n, "advance_share_of_step": adv_ms / prof_ms,
-                         "timed_in": "a separate identical pass with CUDA events around every launch (adds ~7 % to a step); value is measured without them",
-                         "peak_source": peaks["source"]})
-
+            roofline["traffic"] = json.load(f).get("k_glm_tc_main", {}).get("dram_bytes_per_launch")
     cpu = None
-    if world == 1 and not args.skip_cpu:
+    if ctx.world == 1 and not args.skip_cpu:
         cores = args.cpu_cores or os.cpu_count()
         v, done, dt = cpu_reference_run(wl, steps=10 ** 6, warmup=1, budget_s=args.cpu_budget, cores=cores)
         cpu = {"value": v, "unit": "grad-evals/s", "cores": cores, "kind": "port",
-               "sample": "%d tuning transitions on each of %d chains (1 process/chain, full data), %.1f s"
-                         % (done, cores, dt)}
-
-    line = {
-        "metric": "leapfrog_grad_evals_per_sec", "value": value, "unit": "grad-evals/s", "n_gpus": world,
+               "sample": "%d tuning transitions on each of %d chains (1 process/chain, full data), %.1f s" % (done, cores, dt)}
+    job_s = t_timed + secs[2]
+    return {
+        "metric": "leapfrog_grad_evals_per_sec", "value": value, "unit": "grad-evals/s", "n_gpus": ctx.world,
         "steps": K, "warmup": W, "ms_per_step": t_timed * 1e3 / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-        "config": {"workload": wl["label"], "chains_per_gpu": chains, "chains_total": chains * world,
+        "config": {"workload": wl["label"], "chains_per_gpu": chains, "chains_total": chains * ctx.world,
                    "iters_per_step": ips, "tune": tune, "draws": total - tune, "sampler": "NUTS target_accept=0.8",
-                   "l2": L2_NOTES.get(args.workload, "inputs change every launch"),
-                   "grad_evals_counted": "engine leapfrog counters read before and after the timed steps",
-                   "step_boundaries": ("lock-step chains that finish a step early run ahead into the next step's rows; a step "
-                                       "ends when every chain has done its transitions" if ahead else "all chains stop at every step boundary")},
-        # whole sampling job incl. tuning (mirrors benchmarks/benchmarks/benchmarks.py:163-169)
-        "min_bulk_ess_per_sec": (ess_info["min_bulk_ess"] / (t_timed + float(t_vec[2].item()))
-                                 if ess_info else None),
-        "job_seconds": t_timed + float(t_vec[2].item()),
-        "ess": ess_info,
-        "e2e": {"value": e2e_value, "unit": "grad-evals/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(cnt[2].item()),
-        "failed_chains": int(cnt[3].item()),
-        "clocks": clock_info,
-        "roofline": roofline,
-        "cpu_baseline": cpu,
+                   "l2": L2_NOTES["c2"], "grad_evals_counted": "engine leapfrog counters read before and after the timed steps",
+                   "step_boundaries": ("lock-step chains that finish a step early run ahead into the next step's rows"
+                                       if ahead else "all chains stop at every step boundary")},
+        "min_bulk_ess_per_sec": ess_info["min_bulk_ess"] / job_s if ess_info else None,   # whole job incl. tuning
+        "job_seconds": job_s, "ess": ess_info, "e2e": e2e, "gpu_launches": int(cnt[1]), "failed_chains": int(cnt[2]),
+        "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_c5(args):
+# shortened-but-complete jobs of the other BASELINE.json configs (tune + draws, ESS, roofline, e2e); under --gpus N
+# config 3 and 4 split their chains over the ranks (strong scaling), config 5 shards its rows (weak in rows)
+CONFIG_JOBS = {"c1": dict(chains=4, tune=500, draws=1000), "c3": dict(chains=4096, tune=150, draws=100),
+               "c4": dict(chains=512, tune=150, draws=150)}
+
+
+def run_config(ctx, args, name):
+    peaks = measured_peaks()
+    job = dict(CONFIG_JOBS[name])
+    if name == "c1" and ctx.world > 1:
+        return {"skipped": "4 chains, latency-bound by construction: run at N = 1 only"}
+    wl = make_workload(name, args)
+    res = sample_config(ctx, args, wl, job["chains"], job["tune"], job["draws"], split="strong",
+                        profile_chunks=1 if name == "c3" else 0)
+    prof = res.pop("_profile", None)
+    res["config"] = {"workload": wl["label"], "sampler": "NUTS target_accept=0.8", "l2": L2_NOTES.get(name)}
+    if name == "c3":
+        res["roofline"] = lockstep_roofline(prof, wl, peaks, "hbm")
+    if name == "c4":
+        ach = wl["bytes_per_chain_grad"] * res["value"] / max(ctx.world, 1) / 1e9
+        res["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                           "traffic": None, "kernel": "k_persistent_block (whole NUTS transition loop, one launch per chunk)",
+                           "regime": "SURVEY 8d's 70 KB per chain-grad if the state streamed through HBM, set against the whole-job "
+                                     "rate; the hot state is resident in shared memory, so the kernel is instruction-issue bound, not HBM bound",
+                           "peak_source": peaks["source"]}
+    if name == "c1" and ctx.world == 1 and not args.skip_cpu:
+        res["cpu"] = cpu_ess_run(wl, chains=4, tune=job["tune"], draws=job["draws"])
+        if res.get("min_bulk_ess_per_sec") and res["cpu"].get("min_bulk_ess_per_sec"):
+            res["ess_per_sec_vs_cpu"] = res["min_bulk_ess_per_sec"] / res["cpu"]["min_bulk_ess_per_sec"]
+    return res
+
+
+def cpu_ess_run(wl, chains, tune, draws):
+    """the CPU arm's complete job (oracle port, one process per chain): grad-evals/s and min bulk ESS/s incl. tuning"""
+    from oracle.cpu_sampler import CpuChains
+    from pymc3_b200 import stats as b2stats
+    ndim = wl["model"].ndim
+    tp = wl["model"].dict_to_array(wl["model"].test_point)
+    q0 = np.stack([tp + np.random.default_rng([7, c]).uniform(-1, 1, size=ndim) for c in range(chains)])
+    cc = CpuChains(wl["oracle_factory"], q0, chain_seeds(chains, 0), tune=tune)
+    t0 = time.perf_counter()
+    try:
+        _, _, g1, _ = cc.advance(tune)
+        q, _, g2, _ = cc.advance(draws)
+    finally:
+        cc.close()
+    wall = time.perf_counter() - t0
+    ess = float(np.min(b2stats.ess(q)))
+    return {"kind": "port", "cores": chains, "chains": chains, "tune": tune, "draws": draws, "job_seconds": wall,
+            "value": (g1 + g2) / wall, "unit": "grad-evals/s", "min_bulk_ess": ess, "min_bulk_ess_per_sec": ess / wall}
+
+
+def run_c2_small_ess(ctx, args):
+    """min-bulk-ESS/s of the GPU engine against the CPU arm ON THE SAME JOB: a reduced C2 (N = 20 000, D = 100,
+    200 tune + 200 draws) that the CPU port finishes in ~30 s on 8 cores; the GPU runs it with 1024 chains."""
+    import argparse as _ap
+    a2 = _ap.Namespace(**vars(args))
+    a2.n_obs, a2.n_features, a2.chains = 20000, 100, 0
+    wl = make_workload("c2", a2)
+    gpu = sample_config(ctx, a2, wl, 1024, 200, 200, split="strong")
+    gpu.pop("_profile", None)
+    out = {"workload": wl["label"], "gpu": {k: gpu[k] for k in ("value", "chains_total", "tune", "draws", "job_seconds_wall",
+                                                            "min_bulk_ess_per_sec", "ess", "e2e")}}
+    if ctx.world == 1 and not args.skip_cpu:
+        out["cpu"] = cpu_ess_run(wl, chains=min(8, os.cpu_count() or 8), tune=200, draws=200)
+        out["ess_per_sec_vs_cpu"] = gpu["min_bulk_ess_per_sec"] / out["cpu"]["min_bulk_ess_per_sec"]
+        out["grad_evals_per_sec_vs_cpu"] = gpu["e2e"]["value"] / out["cpu"]["value"]
+    return out
+
+
+def run_b200(args):
+    ctx = Ctx()
+    line = None
+    if args.workload in ("all", "c2"):
+        line = run_c2_headline(ctx, args)
+    elif args.workload == "c5":
+        line = run_c5(ctx, args, rows=args.n_obs or 6250000, tune_draws=None)
+    else:
+        res = run_config(ctx, args, args.workload)
+        if ctx.rank == 0:
+            line = {"metric": "leapfrog_grad_evals_per_sec", "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup,
+                    "higher_is_better": True, "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
+                    "data": "synthetic"}
+            line.update(res)
+    if args.workload == "all":
+        configs = {}
+        for name in [c for c in args.configs.split(",") if c]:
+            t0 = time.perf_counter()
+            try:
+                if name == "c5":
+                    res = run_c5(ctx, args, rows=args.c5_rows, tune_draws=(args.c5_iters // 2, args.c5_iters - args.c5_iters // 2))
+                elif name == "c2s":
+                    res = run_c2_small_ess(ctx, args)
+                else:
+                    res = run_config(ctx, args, name)
+            except Exception as err:                         # a failing side config must not take the headline down
+                if ctx.world > 1:
+                    raise
+                res = {"error": "%s: %s" % (type(err).__name__, str(err)[:300])}
+            if isinstance(res, dict):
+                res["bench_seconds"] = time.perf_counter() - t0
+            configs[name] = res
+            ctx.torch.cuda.empty_cache()
+        if ctx.rank == 0:
+            line["configs"] = configs
+    if ctx.rank == 0 and line is not None:
+        print(json.dumps(line))
+    ctx.close()
+
+
+def run_c5(ctx, args, rows, tune_draws):
     """Config 5: logistic regression with the OBSERVATIONS sharded over the GPUs (weak scaling in rows:
     6.25 M rows x 256 features per GPU = 50 M rows on 8), every rank runs all 256 chains redundantly and
     the ranks all-reduce the packed [C, D+1] (logp, dlogp) partials once per leapfrog over NCCL."""
@@ -467,88 +610,107 @@ def run_c5(args):
     from pymc3_b200 import _capi
     from pymc3_b200.model import LogisticGLM
     from pymc3_b200.sharded import run_lockstep_sharded
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    rows = args.n_obs or 6250000
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     k = args.n_features or 256
     chains = args.chains or 256
+    t_setup = time.perf_counter()
     gen = torch.Generator(device=dev)
     gen.manual_seed(5000 + rank)                                 # shard-keyed stream
     X = torch.randn((rows, k), generator=gen, device=dev, dtype=torch.float32).bfloat16().float()
     beta = torch.as_tensor(np.random.default_rng(5).normal(0, 0.5 / np.sqrt(k / 100.0), size=k), dtype=torch.float32, device=dev)
     y = (torch.rand(rows, generator=gen, device=dev) < torch.sigmoid(0.3 + X @ beta)).float()
     model = LogisticGLM(X, y)
+    passes = 2 if bool(torch.equal(X.bfloat16().float(), X)) else 3     # the wide kernel drops the Q.Xlo / R.Xlo pass when Xlo == 0
     ndim = k + 1
-    ips, K, W = args.iters_per_step, args.steps, args.warmup
-    total = (K + W) * ips
-    tune = total // 2
-    eng = model.engine(chains, dtype=args.dtype, device=local_rank)
+    if tune_draws is None:
+        ips, K, W = args.iters_per_step, args.steps, args.warmup
+        total = (K + W) * ips
+        tune = total // 2
+        warm_iters = W * ips
+    else:
+        tune, draws = tune_draws
+        total = tune + draws
+        warm_iters = 0
+    eng = model.engine(chains, dtype=args.dtype, device=ctx.local_rank)
     eng.set_state(start_points(ndim, chains, 0) * 0.1, chain_seeds(chains, 0), 0.25 / ndim ** 0.25, np.zeros(ndim),
                   np.ones(ndim), 10.0)
-    opts = dict(max_treedepth=10, early_max_treedepth=8, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75, t0=10.0,
-                adapt_step_size=1, adapt_mass=1, path_length=2.0, max_steps=1024, hmc_jitter=0,
-                exec_mode=_capi.B2_EXEC_LOCKSTEP, glm_path={"auto": 0, "group": 1, "simt": 2, "tcgen05": 3}[args.glm_path])
+    opts = nuts_opts(args, exec_mode=_capi.B2_EXEC_LOCKSTEP)
     allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
     trace = eng.alloc_trace(_capi.B2_NUTS, total)
+    del X, y
+    torch.cuda.synchronize(dev)
+    setup_s = time.perf_counter() - t_setup
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for s in range(W):
-        run_lockstep_sharded(eng, _capi.B2_NUTS, ips, tune, opts, allreduce, world, out=trace, row0=s * ips)
-    barrier()
+    chunk = 10 if tune_draws is not None else args.iters_per_step
+    done = 0
+    while done < warm_iters:
+        run_lockstep_sharded(eng, _capi.B2_NUTS, chunk, tune, opts, allreduce, world, out=trace, row0=done)
+        done += chunk
+    ctx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.kernel_launches()
+    t0 = time.perf_counter()
     ev0.record()
     steps = 0
-    for s in range(K):
-        run_lockstep_sharded(eng, _capi.B2_NUTS, ips, tune, opts, allreduce, world, out=trace, row0=(W + s) * ips)
+    prof = None
+    while done < total:
+        n = min(chunk, total - done)
+        last = done + n >= total
+        out = run_lockstep_sharded(eng, _capi.B2_NUTS, n, tune, opts, allreduce, world, out=trace, row0=done,
+                                   profile=last)
         steps += eng.last_lockstep_steps
+        if last:
+            prof = eng.last_lockstep_profile
+        done += n
     ev1.record()
-    barrier()
+    ctx.barrier()
+    wall = time.perf_counter() - t0
     t_local = ev0.elapsed_time(ev1) / 1e3
-    t_all = torch.tensor([t_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    t_timed = float(t_all.item())
-    leap = int(trace["tree_size"][W * ips:].sum().item())          # replicated chains: count them once
+    secs, _ = ctx.reduce([t_local, wall], [0])
+    t_timed = secs[0]
+    leap = int(trace["tree_size"][warm_iters:].sum().item())          # replicated chains: count them once
     launches = eng.kernel_launches() - launches0
-    if rank == 0:
-        peaks = measured_peaks()
-        per_step = t_timed / max(steps, 1)
-        x_bytes = rows * k * 4.0
-        units = leap / max(steps, 1)                              # chain-gradients a lock-step step really processed
-        flops = 4.0 * rows * (k + 1) * units
-        line = {"metric": "leapfrog_grad_evals_per_sec", "value": leap / t_timed, "unit": "grad-evals/s", "n_gpus": world,
-                "steps": K, "warmup": W, "ms_per_step": t_timed * 1e3 / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-                "config": {"workload": "logistic regression, observations sharded: %d rows x %d features per GPU, %d rows total"
-                           % (rows, k, rows * world), "chains": chains, "iters_per_step": ips, "tune": tune, "draws": total - tune,
-                           "collective": "all-reduce(sum) of [C, D+1] fp64 = %d bytes per leapfrog" % (chains * (k + 1) * 8)},
-                "lockstep_steps_timed": steps, "chain_grads_per_step": units, "ms_per_leapfrog_all_chains": per_step * 1e3, "gpu_launches": launches,
-                "e2e": None,
-                "roofline": {"bound": "hbm", "achieved": x_bytes / per_step / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": x_bytes / per_step / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                             "tensor_achieved_tflops": flops / per_step / 1e12, "tensor_frac": flops / per_step / 1e12 / peaks["tflops"],
-                             "note": "per GPU, whole lock-step step (likelihood + all-reduce + advance); bytes = X shard read once"}}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    ess_info = None
+    if total - tune >= 20:
+        ess_vec, note = device_ess(trace["q"][tune:])
+        ess_info = {"min_bulk_ess": float(np.nanmin(ess_vec)), "n_scalars": int(len(ess_vec)), "over": note,
+                    "caveat": "only %d draws per chain" % (total - tune)}
+    if rank != 0:
+        return None
+    peaks = measured_peaks()
+    per_step = t_timed / max(steps, 1)
+    x_bytes = rows * k * 2.0 * 2                              # bf16 hi | lo tiles are streamed together (lo is all zeros here)
+    units = leap / max(steps, 1)                              # chain-gradients a lock-step step really processed
+    flops = 4.0 * rows * (k + 1) * units
+    res = {"metric": "leapfrog_grad_evals_per_sec", "value": leap / t_timed, "unit": "grad-evals/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_timed * 1e3 / max(args.steps, 1), "higher_is_better": True,
+           "scaling": "weak (rows per GPU fixed)", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
+           "data": "synthetic",
+           "config": {"workload": "logistic regression, observations sharded: %d rows x %d features per GPU, %d rows total"
+                      % (rows, k, rows * world), "chains": chains, "tune": tune, "draws": total - tune,
+                      "collective": "all-reduce(sum) of [C, D+1] fp64 = %d bytes per leapfrog" % (chains * (k + 1) * 8),
+                      "split_passes": passes,
+                      "setup_seconds": setup_s},
+           "lockstep_steps_timed": steps, "chain_grads_per_step": units, "ms_per_leapfrog_all_chains": per_step * 1e3,
+           "gpu_launches": launches, "job_seconds_device": t_timed, "job_seconds_wall": secs[1], "ess": ess_info,
+           "e2e": {"value": leap / secs[1], "unit": "grad-evals/s",
+                   "through": "pymc3_b200.sharded.run_lockstep_sharded (data generated on the device: nothing to upload; the trace "
+                              "stays on the device)"},
+           "roofline": {"bound": "tensor", "achieved": flops / per_step / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                        "frac": flops / per_step / 1e12 / peaks["tflops"], "traffic": None,
+                        "hbm_achieved_gbs": x_bytes / per_step / 1e9, "hbm_frac": x_bytes / per_step / 1e9 / peaks["hbm_gbs"],
+                        "note": "per GPU, whole lock-step step (likelihood + all-reduce + advance); flops = 4 N (D+1) x live chains; "
+                                "bytes = the bf16 X tiles read once per step", "peak_source": peaks["source"]}}
+    if prof:
+        res["step_breakdown_us"] = prof
+    return res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    wl = make_workload(args.workload, args)
+    wl = make_workload("c2" if args.workload == "all" else args.workload, args)
     cores = args.cpu_cores or os.cpu_count()
     v, done, dt = cpu_reference_run(wl, steps=args.steps, warmup=args.warmup, budget_s=args.ref_budget, cores=cores)
     sample = "%d timed steps; step = 1 NUTS tuning transition on each of %d chains (1 process/chain, full data)" % (done, cores)
@@ -571,7 +733,12 @@ def main():
     ap.add_argument("--steps", type=int, default=17)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c3", "c4", "c5"],
+                    help="all = config 2 as the headline line + the other configs as shortened complete jobs under 'configs'")
+    ap.add_argument("--configs", default="c1,c3,c4,c5,c2s", help="side configs of --workload all (c2s = reduced C2 for the CPU ESS/s ratio)")
+    ap.add_argument("--c5-rows", type=int, default=6250000, help="rows per GPU of the side config c5")
+    ap.add_argument("--c5-iters", type=int, default=30, help="transitions (tune + draws) of the side config c5")
+    ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--iters-per-step", type=int, default=100)
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--n-obs", type=int, default=0)
@@ -593,8 +760,6 @@ def main():
         args.warmup = 3                      # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "c5":
-        run_c5(args)
     else:
         run_b200(args)
 

@@ -706,7 +706,7 @@ struct TcHostState {
     TcWorkspace full;          // every chain in one workspace: b2_logp_dlogp, the stepwise API, the two-kernel step
     TcWorkspace half[2];       // fused lock-step: chains [0, h) | [h, C), one likelihood launch each per leapfrog
     bool pending[2];           // half's likelihood has run, its state machine has not consumed the partials yet
-    bool fused;                // B2_TC_FUSED (default 1)
+    bool fused;                // B2_TC_FUSED (default 0)
     int epi;                   // B2_TC_EPI   (default 1)
     int stages_fused;          // X ring depth of the fused kernel (5, or 4 when the state-machine warps need the room)
     int post_levels;
@@ -778,7 +778,10 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
         B2_CUDA_OK(cudaMalloc(&shared.role_clk, 8 * sizeof(long long)));
         B2_CUDA_OK(cudaMemsetAsync(shared.role_clk, 0, 8 * sizeof(long long), stream));
     }
-    hs->fused = env_int("B2_TC_FUSED", 1) != 0 && !shared.dbg;      // the timeline tools read the two-kernel step
+    // Default: the two-kernel step.  The fused launch measured SLOWER on B200 (round 2, profiles/README.md): the
+    // state-machine warps' shuffles and shared-memory accesses queue behind the epilogue's MUFU / TMEM traffic in the
+    // SM's MIO pipe and a transition end takes 150-185 k cycles instead of ~50 k stand-alone.
+    hs->fused = env_int("B2_TC_FUSED", 0) != 0 && !shared.dbg;      // the timeline tools read the two-kernel step
     hs->epi = env_int("B2_TC_EPI", 1) != 0 ? 1 : 0;
     // shared memory of the fused launch: X ring + the four state-machine warps (hot slots + staged merge levels);
     // prefer the deeper ring, stage as many merge levels as still fit

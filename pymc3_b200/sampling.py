@@ -8,6 +8,7 @@ back in bulk.  Everything around that (argument normalisation, per-chain seeds, 
 `discard_tuned_samples`, MultiTrace, report, convergence checks, errors) keeps the reference's
 behaviour.  Chains shard over `devices` with no communication.
 """
+import collections
 import logging
 import threading
 import time
@@ -40,11 +41,14 @@ def _cpu_count():
 def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=None, chain_idx=0,
            chains=None, cores=None, tune=500, progressbar=True, model=None, random_seed=None,
            discard_tuned_samples=True, compute_convergence_checks=True, callback=None, devices=None,
-           **kwargs):
+           chunk=None, **kwargs):
     """Draw samples from the posterior using the given step method (sampling.py:230).
 
     `cores` is accepted for signature compatibility; chain parallelism is the GPU's.
     `devices`: CUDA device indices to shard chains over (default: the step's device).
+    `callback(trace, draw)` is called for every chain and draw (sampling.py:1396-1398) after each chunk of `chunk`
+    transitions (default: 1 with a callback, else 100); raising KeyboardInterrupt in it, or pressing Ctrl-C,
+    returns the draws completed so far (sampling.py:1407-1409).
     Extra keyword arguments configure the auto-assigned NUTS sampler (sampling.py:439-451).
     """
     model = modelcontext(model)
@@ -100,7 +104,8 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
         start = [{k: v for k, v in trace.point(-1, chain=c).items() if k in model.free_RVs} for c in trace.chains]
 
     t_start = time.time()
-    mtrace = _sample_batched(step, model, draws, tune, chains, start, random_seed, devices, chain_idx)
+    mtrace = _sample_batched(step, model, draws, tune, chains, start, random_seed, devices, chain_idx,
+                             callback=callback, chunk=chunk)
     t_sampling = time.time() - t_start
 
     discard = tune if discard_tuned_samples else 0
@@ -108,10 +113,10 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
     if trace is not None:
         mtrace = _append_traces(trace, mtrace)
     mtrace.report._n_tune = int(tune)
-    mtrace.report._n_draws = int(draws - tune)
+    mtrace.report._n_draws = int(max(0, len(mtrace) - (0 if discard_tuned_samples else tune)))
     mtrace.report._t_sampling = t_sampling
     if compute_convergence_checks:
-        if draws - tune < 100:
+        if len(mtrace) - (0 if discard_tuned_samples else tune) < 100:
             _log.warning("The number of samples is too small to check convergence reliably.")
         else:
             mtrace.report._run_convergence_checks(mtrace, model)
@@ -150,50 +155,196 @@ def _check_start_shape(model, start):
 
 def _start_array(model, start, chains):
     out = np.empty((chains, model.ndim))
+    test_point = model.test_point
+    last, last_row = None, None
     for c in range(chains):
-        point = dict(model.test_point)
+        if start[c] is last:                      # the same dict for every chain (start=None, a single start point)
+            out[c] = last_row
+            continue
+        point = dict(test_point)
         point.update({k: v for k, v in start[c].items() if k in point})       # update_start_vals
         out[c] = model.dict_to_array(point)
+        last, last_row = start[c], out[c]
     return out
 
 
-def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, chain_idx=0):
-    """All chains in one engine per device; chains are split contiguously over devices."""
+Draw = collections.namedtuple("Draw", ["chain", "is_last", "draw_idx", "tuning", "stats", "point", "warnings"])
+"""What `callback(trace=, draw=)` receives -- the fields of pymc3/parallel_sampling.py:348-351."""
+
+
+def _choose_chains(traces, tune):
+    """sampling.py:1417-1443: after an interrupt keep the set of chains that maximises the number of draws."""
+    if tune is None:
+        tune = 0
+    if not traces:
+        return []
+    lengths = [max(0, len(trace) - tune) for trace in traces]
+    if not sum(lengths):
+        raise ValueError("Not enough samples to build a trace.")
+    idxs = np.argsort(lengths)[::-1]
+    l_sort = np.array(lengths)[idxs]
+    final_length = l_sort[0]
+    last_total = 0
+    for i, length in enumerate(l_sort):
+        total = (i + 1) * length
+        if total < last_total:
+            use_until = i
+            break
+        last_total = total
+        final_length = length
+    else:
+        use_until = len(lengths)
+    return [traces[idx] for idx in idxs[:use_until]], final_length + tune
+
+
+class _ShardRun:
+    """One device's share of the chains: engine, device trace for the whole job, and a host copy that is
+    filled chunk by chunk through two pinned staging buffers (the device -> host copy of chunk i overlaps
+    the sampling of chunk i + 1)."""
+
+    def __init__(self, step, dev, q0, seeds, draws):
+        import torch
+        self.torch, self.step, self.draws = torch, step, draws
+        self.eng = step._make_engine(len(q0), device=dev)
+        step._init_engine_state(self.eng, q0, seeds)
+        self.trace = self.eng.alloc_trace(step._kind, draws)
+        self.host = {k: np.empty(tuple(v.shape), dtype=_np_dtype(v)) for k, v in self.trace.items()}
+        self.copy_stream = torch.cuda.Stream(device=self.eng.dev)
+        self.staging = [None, None]
+        self.pending = []                     # (rows, staging index, event)
+        self.rows_done = 0
+        self._k = 0
+        self.device_seconds = 0.0
+        self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    def _flush(self, keep=0):
+        while len(self.pending) > keep:
+            (lo, hi), k, ev = self.pending.pop(0)
+            ev.synchronize()
+            for name, buf in self.staging[k].items():
+                self.host[name][lo:hi] = buf[: hi - lo].numpy()
+
+    def run_chunk(self, n, tune, run_ahead):
+        """`n` more transitions of every chain of this shard; returns the host rows [lo, hi) now complete."""
+        torch = self.torch
+        lo, hi = self.rows_done, self.rows_done + n
+        with torch.cuda.device(self.eng.dev):
+            self._ev[0].record()
+            self.eng.run(self.step._kind, n, tune, self.step._opts(), out=self.trace, row0=lo, run_ahead=run_ahead)
+            self._ev[1].record()
+            self._k ^= 1
+            k = self._k
+            self._flush(keep=1)               # only the previous chunk (other buffer) may still be in flight
+            if self.staging[k] is None or next(iter(self.staging[k].values())).shape[0] < n:
+                self.staging[k] = {name: torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True)
+                                   for name, t in self.trace.items()}
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.eng.dev))
+            with torch.cuda.stream(self.copy_stream):
+                for name, t in self.trace.items():
+                    self.staging[k][name][:n].copy_(t[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            self.pending.append(((lo, hi), k, ev))
+            self._ev[1].synchronize()
+            self.device_seconds += self._ev[0].elapsed_time(self._ev[1]) / 1e3
+        self.rows_done = hi
+        return lo, hi
+
+    def finish(self):
+        self._flush(keep=0)
+        out = (self.eng.reports(), self.eng.mass_var(), self.eng.kernel_launches())
+        self.eng.close()
+        self.trace = None
+        return out
+
+
+def _np_dtype(t):
+    import torch
+    return {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8,
+            torch.int64: np.int64}[t.dtype]
+
+
+def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, chain_idx=0, callback=None,
+                    chunk=None):
+    """All chains in one engine per device; chains are split contiguously over devices.
+
+    The job runs in chunks of `chunk` transitions (default 100; 1 when a `callback` is given, so that it sees
+    every draw like the reference's per-draw loop, sampling.py:1384-1398): chains that finish a chunk early run
+    ahead into the following rows of the preallocated device trace, each finished chunk is copied to the host
+    while the next one samples, `callback(trace=, draw=)` is called per chain and draw of the chunk, and a
+    KeyboardInterrupt (from the callback or the user) returns what is complete so far, chosen like
+    sampling.py:1407-1443."""
     devices = list(devices) if devices is not None else [step.device]
     q0 = _start_array(model, start, chains)
     seeds = np.asarray(seeds, dtype=np.uint64)
     bounds = np.linspace(0, chains, len(devices) + 1).astype(int)
     shards = [(dev, bounds[i], bounds[i + 1]) for i, dev in enumerate(devices) if bounds[i + 1] > bounds[i]]
-    results = [None] * len(shards)
-    errors = []
+    if chunk is None:
+        chunk = 1 if callback is not None else 100
+    chunk = max(1, min(int(chunk), draws))
+    runs = [_ShardRun(step, dev, q0[lo:hi], seeds[lo:hi], draws) for dev, lo, hi in shards]
+    stat_dtypes = step.stats_dtypes[0]
+    interrupted = False
+    done = 0
 
-    def work(k, dev, lo, hi):
-        try:
-            eng = step._make_engine(hi - lo, device=dev)
-            step._init_engine_state(eng, q0[lo:hi], seeds[lo:hi])
-            out = eng.run(step._kind, draws, tune, step._opts())
-            host = {name: t.cpu().numpy() for name, t in out.items()}
-            results[k] = (host, eng.reports(), eng.mass_var(), eng.kernel_launches())
-            eng.close()
-        except Exception as err:  # surfaced on the caller's thread
-            errors.append(err)
+    def run_all(n):
+        errors = []
+        if len(runs) == 1:
+            runs[0].run_chunk(n, tune, True)
+            return
 
-    if len(shards) == 1:
-        work(0, *shards[0])
-    else:
-        threads = [threading.Thread(target=work, args=(k,) + sh) for k, sh in enumerate(shards)]
+        def work(r):
+            try:
+                r.run_chunk(n, tune, True)
+            except BaseException as err:      # surfaced on the caller's thread
+                errors.append(err)
+        threads = [threading.Thread(target=work, args=(r,)) for r in runs]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
-    if errors:
-        raise errors[0]
+        if errors:
+            raise errors[0]
 
-    host = {name: np.concatenate([r[0][name] for r in results], axis=1) for name in results[0][0]}
-    reports = [rep for r in results for rep in r[1]]
-    mass_var = np.concatenate([r[2] for r in results])
-    step._last_kernel_launches = sum(r[3] for r in results)
+    # bench.py hook: time the individual likelihood / advance launches of the last chunks of the job
+    n_chunks = (draws + chunk - 1) // chunk
+    prof_from = n_chunks - int(getattr(step, "_profile_last_chunks", 0) or 0)
+    prof = None
+    try:
+        while done < draws:
+            n = min(chunk, draws - done)
+            if done // chunk == prof_from and prof_from >= 0 and prof is None:
+                for r in runs:
+                    r.eng.set_profiling(True)
+                prof = {"n_grad0": sum(rep.n_grad for r in runs for rep in r.eng.reports()), "t0": time.perf_counter()}
+            run_all(n)
+            done += n
+            if callback is not None:
+                for r in runs:
+                    r._flush(keep=0)
+                _chunk_callbacks(callback, step, model, runs, shards, done - n, done, draws, tune, chain_idx, stat_dtypes)
+    except KeyboardInterrupt:
+        interrupted = True
+
+    if prof is not None:
+        like = [r.eng.profile() for r in runs]
+        prof.update(seconds=time.perf_counter() - prof["t0"],
+                    n_grad=sum(rep.n_grad for r in runs for rep in r.eng.reports()) - prof["n_grad0"],
+                    like_ms=sum(x[0] for x in like), like_n=sum(x[1] for x in like),
+                    adv_ms=sum(r.eng.profile_advance() for r in runs), shards=len(runs))
+    step._last_profile = prof
+    results = [r.finish() for r in runs]
+    rows = min(r.rows_done for r in runs) if not interrupted else done
+    if len(runs) == 1:
+        host = {name: arr[:rows] for name, arr in runs[0].host.items()}
+    else:
+        host = {name: np.concatenate([r.host[name][:rows] for r in runs], axis=1) for name in runs[0].host}
+    reports = [rep for r in results for rep in r[0]]
+    mass_var = np.concatenate([r[1] for r in results])
+    step._last_kernel_launches = sum(r[2] for r in results)
     step._last_reports = reports
+    step._last_device_seconds = max(r.device_seconds for r in runs)
+    step._last_n_grad = int(sum(rep.n_grad for rep in reports))
 
     for c, rep in enumerate(reports):
         if rep.phase == _capi.PHASE_FAILED:
@@ -202,30 +353,17 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
             except SamplingError as err:
                 raise SamplingError("Bad initial energy (chain %d)" % (chain_idx + c)) from err
 
-    # [draws, C, D] -> per-variable [C, draws, *shape] (vectorised replacement of ndarray.py:266)
-    q = np.ascontiguousarray(np.swapaxes(host.pop("q"), 0, 1)).astype("f8")
-    values = model.expand(q)
-    stat_dtypes = step.stats_dtypes[0]
-    stats = {}
-    for key, dt in stat_dtypes.items():
-        if key == "path_length":
-            stats[key] = np.full((chains, draws), float(step.path_length))
-        else:
-            stats[key] = np.ascontiguousarray(host[key].T).astype(dt)
-    accept_key = "mean_tree_accept" if "mean_tree_accept" in stats else "accept"
-    straces = []
-    for c in range(chains):
-        st = NDArray.from_arrays(model, chain_idx + c, {n: v[c] for n, v in values.items()},
-                                 {k: v[c] for k, v in stats.items()})
-        st._add_warnings(step._chain_warnings(reports[c], stats[accept_key][c, tune:], stats["diverging"][c],
-                                              stats["tune"][c]))
-        straces.append(st)
+    straces = _bulk_straces(step, model, host, reports, rows, tune, chains, chain_idx, stat_dtypes)
+    if interrupted:
+        straces, length = _choose_chains(straces, tune)
+        return MultiTrace(straces)[:length]
 
     # leave the step object in the state the reference's would be in after sampling
+    accept_key = "mean_tree_accept" if "mean_tree_accept" in host else "accept"
     step.iter_count = draws
     step.tune = not (tune < draws)
     step.step_size = float(reports[0].step_size)
-    step.step_adapt.sync(reports[0].step_size, reports[0].step_size_bar, stats[accept_key][0, tune:])
+    step.step_adapt.sync(reports[0].step_size, reports[0].step_size_bar, host[accept_key][tune:, 0])
     step._samples_after_tune = reports[0].n_post
     step._num_divs_sample = reports[0].n_div_post
     if hasattr(step, "_reached_max_treedepth"):
@@ -233,6 +371,49 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     if hasattr(step.potential, "sync"):
         step.potential.sync(mass_var[0])
     return MultiTrace(straces)
+
+
+def _bulk_straces(step, model, host, reports, rows, tune, chains, chain_idx, stat_dtypes):
+    """[rows, C, D] host trace -> one NDArray per chain holding VIEWS of the bulk arrays (vectorised replacement of
+    the per-draw record() of ndarray.py:258-277; no per-draw Python work, no dtype round trip)."""
+    q = np.ascontiguousarray(np.swapaxes(host["q"], 0, 1))          # [C, rows, D], engine dtype
+    values = model.expand(q)
+    stats = {}
+    for key, dt in stat_dtypes.items():
+        if key == "path_length":
+            stats[key] = np.full((chains, rows), float(step.path_length))
+        else:
+            stats[key] = np.ascontiguousarray(host[key].T).astype(dt, copy=False)
+    accept_key = "mean_tree_accept" if "mean_tree_accept" in stats else "accept"
+    # sampler warnings for all chains from bulk reductions; per-draw divergence records only where there are any
+    div_rows = [np.nonzero(stats["diverging"][c])[0] for c in range(chains)] if stats["diverging"].any() else None
+    n_post = max(0, rows - tune)
+    mean_acc = stats[accept_key][:, tune:].mean(axis=1) if n_post else np.full(chains, np.nan)
+    straces = []
+    for c in range(chains):
+        st = NDArray.from_arrays(model, chain_idx + c, {n: v[c] for n, v in values.items()},
+                                 {k: v[c] for k, v in stats.items()})
+        st._add_warnings(step._chain_warnings(reports[c], mean_acc[c], n_post,
+                                              div_rows[c] if div_rows is not None else (), stats["tune"][c]))
+        straces.append(st)
+    return straces
+
+
+def _chunk_callbacks(callback, step, model, runs, shards, lo, hi, draws, tune, chain_idx, stat_dtypes):
+    """callback(trace=, draw=) for every chain and every draw of rows [lo, hi), in the reference's shape: `trace`
+    is the chain's trace up to and including the draw (len(trace) works), `draw` a Draw tuple."""
+    for r, (dev, c_lo, c_hi) in zip(runs, shards):
+        q = r.host["q"]
+        for c in range(c_hi - c_lo):
+            for i in range(lo, hi):
+                qc = np.ascontiguousarray(q[: i + 1, c])
+                values = model.expand(qc)
+                stats = {k: (np.full(i + 1, float(step.path_length)) if k == "path_length"
+                             else r.host[k][: i + 1, c].astype(dt, copy=False)) for k, dt in stat_dtypes.items()}
+                st = NDArray.from_arrays(model, chain_idx + c_lo + c, values, stats)
+                point = {k: v[i] for k, v in values.items()}
+                row = {k: v[i] for k, v in stats.items()}
+                callback(trace=st, draw=Draw(chain_idx + c_lo + c, i == draws - 1, i, i < tune, [row], point, None))
 
 
 def iter_sample(draws, step, start=None, trace=None, chain=0, tune=None, model=None, random_seed=None,

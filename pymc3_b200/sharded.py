@@ -25,9 +25,11 @@ def row_shard(n_rows, world_size, rank):
 
 
 def run_lockstep_sharded(engine, kind, n_iters, tune_until, opts, allreduce, world_size, check_every=16,
-                         out=None, row0=0):
+                         out=None, row0=0, profile=False):
     """Drives `n_iters` transitions of all chains of `engine` (this rank's shard) in lock-step with the
-    other ranks.  Returns the device trace dict (identical on every rank)."""
+    other ranks.  Returns the device trace dict (identical on every rank).  `profile`: CUDA events around the
+    three parts of the first 256 leapfrogs; their mean durations land in `engine.last_lockstep_profile`
+    ({"likelihood_us", "allreduce_us", "advance_us", "allreduce_share"})."""
     torch = engine.torch
     lib = engine.lib
     if out is None:
@@ -44,12 +46,24 @@ def run_lockstep_sharded(engine, kind, n_iters, tune_until, opts, allreduce, wor
     _capi.check(lib.b2_step_begin(engine.handle, C.byref(o), C.byref(tr), stream), lib)
     active = C.c_int32(1)
     steps = 0
+    events = []
     while True:
         for _ in range(check_every):
+            timed = profile and len(events) < 256
+            if timed:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
             _capi.check(lib.b2_step_likelihood(engine.handle, packed.data_ptr(), stream), lib)
+            if timed:
+                ev[1].record()
             if world_size > 1:
                 allreduce(packed)
+            if timed:
+                ev[2].record()
             _capi.check(lib.b2_step_advance(engine.handle, packed.data_ptr(), int(world_size), stream), lib)
+            if timed:
+                ev[3].record()
+                events.append(ev)
             steps += 1
         _capi.check(lib.b2_step_active(engine.handle, C.byref(active), stream), lib)
         if active.value == 0:
@@ -57,6 +71,13 @@ def run_lockstep_sharded(engine, kind, n_iters, tune_until, opts, allreduce, wor
     _capi.check(lib.b2_step_end(engine.handle), lib)
     engine.iter_done += int(n_iters)
     engine.last_lockstep_steps = steps
+    engine.last_lockstep_profile = None
+    if events:
+        torch.cuda.synchronize(engine.dev)
+        parts = np.array([[e[i].elapsed_time(e[i + 1]) * 1e3 for i in range(3)] for e in events]).mean(axis=0)
+        engine.last_lockstep_profile = {"likelihood_us": float(parts[0]), "allreduce_us": float(parts[1]),
+                                        "advance_us": float(parts[2]), "allreduce_share": float(parts[1] / parts.sum()),
+                                        "leapfrogs_timed": len(events)}
     return view
 
 

@@ -211,15 +211,14 @@ class BaseHMC:
         warnings.extend(self.step_adapt.warnings())
         return warnings
 
-    def _chain_warnings(self, report, accept_post, diverging, tune_flags):
-        """Warnings of one chain of a batched run, from its device report and stats."""
+    def _chain_warnings(self, report, mean_accept_post, n_post, diverging_rows, tune_flags):
+        """Warnings of one chain of a batched run, from its device report and bulk reductions of its stats
+        (`mean_accept_post`: mean acceptance statistic of the `n_post` post-tuning draws; `diverging_rows`: indices)."""
         warns = []
-        for i in np.nonzero(diverging)[0]:
+        for i in diverging_rows:
             kind = WarningType.TUNING_DIVERGENCE if tune_flags[i] else WarningType.DIVERGENCE
             warns.append(SamplerWarning(kind, "Energy change in leapfrog step is too large.", "debug",
                                         int(i), None, None))
         warns.extend(self._divergence_summary(report.n_div_post, report.n_post))
-        da = step_sizes.DualAverageAdaptation(self._initial_step, self.target_accept, *self._da)
-        da._tuned_stats = list(accept_post)
-        warns.extend(da.warnings())
+        warns.extend(step_sizes.acceptance_warnings(mean_accept_post, n_post, self.target_accept))
         return warns

@@ -10,6 +10,22 @@ from scipy import stats
 from ..backends.report import SamplerWarning, WarningType
 
 
+def acceptance_warnings(mean_accept, n_draws, target):
+    """step_sizes.py:60-79: is the target inside the 95 % beta interval of the mean acceptance rate, counted over
+    (at most) 100 draws?"""
+    if not n_draws or not np.isfinite(mean_accept):
+        return []
+    n_bound = min(100, int(n_draws))
+    n_good, n_bad = mean_accept * n_bound, (1 - mean_accept) * n_bound
+    lower, upper = stats.beta(n_good + 1, n_bad + 1).interval(0.95)
+    if target < lower or target > upper:
+        msg = ("The acceptance probability does not match the target. It is %s, but should be close "
+               "to %s. Try to increase the number of tuning steps." % (mean_accept, target))
+        info = {"target": target, "actual": mean_accept}
+        return [SamplerWarning(WarningType.BAD_ACCEPTANCE, msg, "warn", None, None, info)]
+    return []
+
+
 class DualAverageAdaptation:
     def __init__(self, initial_step, target, gamma, k, t0):
         self._initial_step = initial_step
@@ -35,13 +51,4 @@ class DualAverageAdaptation:
         accept = np.array(self._tuned_stats)
         if accept.size == 0:
             return []
-        mean_accept = np.mean(accept)
-        n_bound = min(100, len(accept))
-        n_good, n_bad = mean_accept * n_bound, (1 - mean_accept) * n_bound
-        lower, upper = stats.beta(n_good + 1, n_bad + 1).interval(0.95)
-        if self._target < lower or self._target > upper:
-            msg = ("The acceptance probability does not match the target. It is %s, but should be close "
-                   "to %s. Try to increase the number of tuning steps." % (mean_accept, self._target))
-            info = {"target": self._target, "actual": mean_accept}
-            return [SamplerWarning(WarningType.BAD_ACCEPTANCE, msg, "warn", None, None, info)]
-        return []
+        return acceptance_warnings(float(np.mean(accept)), len(accept), self._target)
