@@ -30,7 +30,8 @@ class NDArray(base.BaseTrace):
     @classmethod
     def from_arrays(cls, model, chain, samples, stats):
         """samples: {varname: [draws, *shape]}, stats: {stat: [draws]} for one chain."""
-        self = cls(model=model)
+        self = cls()                          # no model introspection: names, shapes and dtypes come from the arrays
+        self.model = model                    # (thousands of chains are adopted per run)
         self.chain = chain
         self.samples = dict(samples)
         self.varnames = list(samples.keys())
@@ -102,9 +103,10 @@ class NDArray(base.BaseTrace):
         return self.samples[varname][burn::thin]
 
     def _slice(self, idx):
-        if idx.start is None and idx.stop is None and idx.step is None:
+        if idx.start in (None, 0) and idx.stop is None and idx.step in (None, 1):
             return self
-        sliced = NDArray(model=self.model)
+        sliced = NDArray()
+        sliced.model = self.model
         sliced.chain = self.chain
         sliced.varnames = list(self.varnames)
         sliced.var_shapes, sliced.var_dtypes = self.var_shapes, self.var_dtypes

@@ -71,6 +71,7 @@ struct TcWorkspace {
     int n_tiles, c_pad, chain_tiles, splits, tiles_per_split, n_pad_rows;
     int first, count;        // the chains this workspace covers: [first, first + count)
     int post_levels;         // merge levels whose stack buffers the state-machine warps stage in shared memory
+    int flush_tiles;         // the gradient accumulator is drained into the fp32 partials every flush_tiles tiles
     int* err;                // device watchdog flag
     long long* role_clk;     // optional (B2_TC_ROLE_CLOCKS=1): {sum, count, max} cycles of the state-machine warps, then of the likelihood CTAs
     // per launch: where every chain's pending position lives
@@ -421,8 +422,9 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
     uint64_t* s_empty = s_full + 2;                // 2
     uint64_t* p_full = s_empty + 2;                // 2
     uint64_t* p_empty = p_full + 2;                // 2
-    uint64_t* g_full = p_empty + 2;                // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
+    uint64_t* g_full = p_empty + 2;                // 1: completes once per flush chunk (GEMM2 of the chunk's last tile)
+    uint64_t* g_empty = g_full + 1;                // 1: every epilogue warp has read the chunk's G out of TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (FUSED && warp >= TC_THREADS / 32) {
@@ -458,6 +460,7 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
             for (int i = 0; i < STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TC_EPI_WARPS / 2); mbar_init(p_full + i, TC_EPI_WARPS / 2); mbar_init(p_empty + i, 1); }
             mbar_init(g_full, 1);
+            mbar_init(g_empty, TC_EPI_WARPS);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 2) {
@@ -528,10 +531,16 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
             // N = features rounded up to 16 (UMMA N granularity at M = 128): 112 instead of 128 at D+1 = 101
             const uint32_t n2 = (uint32_t)((ws.K1 + 15) & ~15);
             const uint32_t idesc_g2 = TC_IDESC_BASE | (1u << 16) | ((n2 >> 3) << 17) | ((TC_CHAINS >> 4) << 24);
+            // The accumulator adds with truncation (up to an ulp of the RUNNING sum per MMA, towards zero): 1044 adds
+            // into one G biased the gradient by 1e-4 of its size near the posterior mode (round 2 parity test at C2
+            // size), so G is drained into the slab's fp32 partial (round-to-nearest adds) every F tiles.
+            const int F = ws.flush_tiles;
             for (int u = 0; u < T; ++u) {
                 const int s = u % STAGES, b = u & 1;
+                const bool chunk_first = (u % F) == 0, chunk_last = ((u + 1) % F) == 0 || u == T - 1;
                 if (lane == 0) TC_STAMP(2, u);
                 mbar_wait(p_full + b, (u >> 1) & 1, ws.err, 5);
+                if (chunk_first && u > 0) mbar_wait(g_empty, ((u / F) - 1) & 1, ws.err, 10);   // the previous chunk's G has been read out
                 tc_fence_after();
                 const uint32_t x_addr = smem_u32(x_s + s * TC_STAGE_BYTES);
                 const uint32_t p_base = tmem + TC_COL_P + 64 * b;
@@ -545,12 +554,12 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
                         for (int j = 0; j < TC_OBS / 16; ++j) {
                             // MN-major B: 2 feature atoms LBO = 8192 B apart, 8-row groups SBO = 1024 B apart
                             const uint64_t bd = make_desc(xa + j * 2048, TC_OBS * 128, 1024);
-                            mma_ts(d, pa + j * 8, bd, idesc_g2, (u > 0 || pass > 0 || j > 0) ? 1u : 0u);
+                            mma_ts(d, pa + j * 8, bd, idesc_g2, (!chunk_first || pass > 0 || j > 0) ? 1u : 0u);
                         }
                     }
                     tc_commit(x_empty + s);
                     tc_commit(p_empty + b);
-                    if (u == T - 1) tc_commit(g_full);
+                    if (chunk_last) tc_commit(g_full);
                     TC_STAMP(3, u);
                 }
                 __syncwarp();
@@ -609,7 +618,37 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
         }
         const int pair = cg >> 1, sub = cg & 1;
         float lp_sum = 0.f, lp_comp = 0.f;                         // Kahan: no FP64 adds in the tile loop (ncu r1b)
+        // Chunked gradient accumulation (see the GEMM2 issuer): after GEMM2 of a chunk's last tile every epilogue
+        // warp adds its 32 columns of G into the slab's fp32 partial in global memory -- the same thread owns the
+        // same elements every time, so plain load-add-store -- and releases the accumulator.
+        const int F = ws.flush_tiles;
+        const int n_chunks = (T + F - 1) / F;
+        int k_drain = 0;                                           // next chunk this warp has to drain
+        float* gout = ws.gpart + ((size_t)split * gm.stride + ctile * TC_CHAINS + row) * TC_KP + 32 * cg;
+        auto drain = [&](int k) {
+            mbar_wait(g_full, k & 1, ws.err, 8);
+            tc_fence_after();
+            uint32_t g32[32];
+            TC_LD32(tmem + lane_addr + TC_COL_G + 32 * cg, g32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(g_empty);                   // G is in registers: the next chunk may start
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 a = make_float4(__uint_as_float(g32[4 * i]), __uint_as_float(g32[4 * i + 1]),
+                                       __uint_as_float(g32[4 * i + 2]), __uint_as_float(g32[4 * i + 3]));
+                if (k > 0) {
+                    const float4 o = reinterpret_cast<const float4*>(gout)[i];
+                    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                }
+                reinterpret_cast<float4*>(gout)[i] = a;
+            }
+        };
         for (int t = pair; t < T; t += 2) {
+            // before touching a tile of a new chunk, drain the chunks that end before it (draining after the tile
+            // instead can deadlock: GEMM2 of the next chunk waits for all sixteen warps, see b2_glm_tcw.cu)
+            while (k_drain < n_chunks - 1 && (k_drain + 1) * F - 1 < t) { drain(k_drain); ++k_drain; }
             const int s = t % STAGES, b = pair;
             // this warp's 32 observations of the stage's y block: y (EPI 0) or y - 1/2 (EPI 1)
             const uint32_t ys_addr = smem_u32(y_s + s * TC_Y_BYTES) + (EPI ? TC_OBS * 4 : 0) + 128 * sub;
@@ -653,21 +692,9 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
             lp_sum = kt;
         }
         const double logp = (double)lp_sum - (double)lp_comp;
-        // the slab's gradient tile: G[chain row][128 features] -> global partials (32 columns per group)
-        mbar_wait(g_full, 0, ws.err, 8);
-        tc_fence_after();
+        // what is left: at least the last chunk, G[chain row][128 features] -> global partials (32 columns per group)
+        while (k_drain < n_chunks) { drain(k_drain); ++k_drain; }
         const int slot = ctile * TC_CHAINS + row;
-        float* gout = ws.gpart + ((size_t)split * gm.stride + slot) * TC_KP + 32 * cg;
-        {
-            uint32_t g32[32];
-            TC_LD32(tmem + lane_addr + TC_COL_G + 32 * cg, g32);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(gout)[i] =
-                    make_float4(__uint_as_float(g32[4 * i]), __uint_as_float(g32[4 * i + 1]),
-                                __uint_as_float(g32[4 * i + 2]), __uint_as_float(g32[4 * i + 3]));
-        }
         // logp partial of this column group; the finalize kernel adds the TC_EPI_GROUPS partials
         ws.lpart[((size_t)split * TC_EPI_GROUPS + cg) * gm.stride + slot] = logp;
         tc_fence_before();
@@ -767,6 +794,8 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     const int N = e->md.N;
     shared.n_tiles = (N + TC_OBS - 1) / TC_OBS;
     shared.n_pad_rows = shared.n_tiles * TC_OBS - N;
+    shared.flush_tiles = env_int("B2_TC_FLUSH", 32);           // 12 MMAs per tile: <= 384 truncating adds per drain
+    if (shared.flush_tiles < 4) shared.flush_tiles = 4;
     B2_CUDA_OK(cudaMalloc(&shared.xt, (size_t)shared.n_tiles * TC_STAGE_DATA));
     B2_CUDA_OK(cudaMalloc(&shared.err, TC_ERR_INTS * sizeof(int)));
     B2_CUDA_OK(cudaMemsetAsync(shared.err, 0, TC_ERR_INTS * sizeof(int), stream));

@@ -186,8 +186,11 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
                 const int s = t % TW_STAGES;
                 if (t >= TW_STAGES) mbar_wait(x_empty + s, ((t / TW_STAGES) - 1) & 1, ws.err, 1);
                 const unsigned char* src = ws.xt + (size_t)(t_begin + t) * TW_STAGE_DATA;
-                mbar_expect_tx(x_full + s, TW_STAGE_DATA);
-                bulk_g2s(x_s + s * TW_STAGE_BYTES, src, TW_STAGE_BYTES, x_full + s);
+                // Xlo == 0 (two split passes): only the hi half of the tile is read, which halves the HBM / L2
+                // traffic of a launch -- the bound when few chains are live (C5: 6.4 -> 3.2 GB per leapfrog)
+                const uint32_t x_bytes = ws.n_pass == 2 ? TW_XPART_BYTES : TW_STAGE_BYTES;
+                mbar_expect_tx(x_full + s, x_bytes + TW_Y_BYTES);
+                bulk_g2s(x_s + s * TW_STAGE_BYTES, src, x_bytes, x_full + s);
                 bulk_g2s(y_s + s * TW_Y_BYTES, src + TW_STAGE_BYTES, TW_Y_BYTES, x_full + s);
             }
         }

@@ -21,6 +21,7 @@ from .backends.base import MultiTrace
 from .backends.ndarray import NDArray
 from .exceptions import SamplingError
 from .model import modelcontext
+from .step_methods import step_sizes
 from .step_methods.hmc import NUTS
 from .step_methods.hmc.quadpotential import QuadPotentialDiagAdapt
 
@@ -198,11 +199,14 @@ def _choose_chains(traces, tune):
 
 
 class _ShardRun:
-    """One device's share of the chains: engine, device trace for the whole job, and a host copy that is
-    filled chunk by chunk through two pinned staging buffers (the device -> host copy of chunk i overlaps
-    the sampling of chunk i + 1)."""
+    """One device's share of the chains: engine, device trace for the whole job, and a host copy that a
+    background thread fills chunk by chunk (device -> pinned staging pieces -> host array) while the next chunk
+    samples -- the sampling call releases the GIL, so copies and MCMC overlap."""
+
+    PIECE_BYTES = 48 << 20                    # staging buffers: 2 x 48 MB of pinned memory per shard
 
     def __init__(self, step, dev, q0, seeds, draws):
+        import queue
         import torch
         self.torch, self.step, self.draws = torch, step, draws
         self.eng = step._make_engine(len(q0), device=dev)
@@ -210,48 +214,84 @@ class _ShardRun:
         self.trace = self.eng.alloc_trace(step._kind, draws)
         self.host = {k: np.empty(tuple(v.shape), dtype=_np_dtype(v)) for k, v in self.trace.items()}
         self.copy_stream = torch.cuda.Stream(device=self.eng.dev)
-        self.staging = [None, None]
-        self.pending = []                     # (rows, staging index, event)
         self.rows_done = 0
-        self._k = 0
         self.device_seconds = 0.0
         self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self._jobs = queue.Queue()
+        self._error = None
+        self._thread = threading.Thread(target=self._copier, daemon=True)
+        self._thread.start()
 
-    def _flush(self, keep=0):
-        while len(self.pending) > keep:
-            (lo, hi), k, ev = self.pending.pop(0)
-            ev.synchronize()
-            for name, buf in self.staging[k].items():
-                self.host[name][lo:hi] = buf[: hi - lo].numpy()
+    def _copier(self):
+        torch = self.torch
+        try:
+            torch.cuda.set_device(self.eng.dev)
+            row_bytes = sum(int(np.prod(t.shape[1:])) * t.element_size() for t in self.trace.values())
+            piece = max(1, self.PIECE_BYTES // max(row_bytes, 1))
+            staging = [{name: torch.empty((piece,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True)
+                        for name, t in self.trace.items()} for _ in range(2)]
+            events = [None, None]
+            spans = [None, None]
+
+            def drain(k):
+                if events[k] is not None:
+                    events[k].synchronize()
+                    lo, hi = spans[k]
+                    for name, buf in staging[k].items():
+                        self.host[name][lo:hi] = buf[: hi - lo].numpy()
+                    events[k] = None
+            k = 0
+            while True:
+                job = self._jobs.get()
+                if job is None:
+                    break
+                (lo, hi), ready = job
+                for p_lo in range(lo, hi, piece):
+                    p_hi = min(hi, p_lo + piece)
+                    drain(k)
+                    with torch.cuda.stream(self.copy_stream):
+                        self.copy_stream.wait_event(ready)
+                        for name, t in self.trace.items():
+                            staging[k][name][: p_hi - p_lo].copy_(t[p_lo:p_hi], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self.copy_stream)
+                    events[k], spans[k] = ev, (p_lo, p_hi)
+                    k ^= 1
+            drain(0)
+            drain(1)
+        except BaseException as err:          # surfaced by finish()
+            self._error = err
 
     def run_chunk(self, n, tune, run_ahead):
-        """`n` more transitions of every chain of this shard; returns the host rows [lo, hi) now complete."""
+        """`n` more transitions of every chain of this shard; their rows are handed to the copier thread."""
         torch = self.torch
         lo, hi = self.rows_done, self.rows_done + n
         with torch.cuda.device(self.eng.dev):
             self._ev[0].record()
             self.eng.run(self.step._kind, n, tune, self.step._opts(), out=self.trace, row0=lo, run_ahead=run_ahead)
             self._ev[1].record()
-            self._k ^= 1
-            k = self._k
-            self._flush(keep=1)               # only the previous chunk (other buffer) may still be in flight
-            if self.staging[k] is None or next(iter(self.staging[k].values())).shape[0] < n:
-                self.staging[k] = {name: torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True)
-                                   for name, t in self.trace.items()}
-            self.copy_stream.wait_stream(torch.cuda.current_stream(self.eng.dev))
-            with torch.cuda.stream(self.copy_stream):
-                for name, t in self.trace.items():
-                    self.staging[k][name][:n].copy_(t[lo:hi], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
-            self.pending.append(((lo, hi), k, ev))
+            ready = torch.cuda.Event()
+            ready.record()
+            self._jobs.put(((lo, hi), ready))
             self._ev[1].synchronize()
             self.device_seconds += self._ev[0].elapsed_time(self._ev[1]) / 1e3
         self.rows_done = hi
         return lo, hi
 
+    def flush(self):
+        """block until every row handed over so far is in the host arrays"""
+        self._jobs.put(None)
+        self._thread.join()
+        if self._error is not None:
+            raise self._error
+        self._thread = threading.Thread(target=self._copier, daemon=True)
+        self._thread.start()
+
     def finish(self):
-        self._flush(keep=0)
+        self._jobs.put(None)
+        self._thread.join()
+        if self._error is not None:
+            raise self._error
         out = (self.eng.reports(), self.eng.mass_var(), self.eng.kernel_launches())
         self.eng.close()
         self.trace = None
@@ -321,7 +361,7 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
             done += n
             if callback is not None:
                 for r in runs:
-                    r._flush(keep=0)
+                    r.flush()
                 _chunk_callbacks(callback, step, model, runs, shards, done - n, done, draws, tune, chain_idx, stat_dtypes)
     except KeyboardInterrupt:
         interrupted = True
@@ -376,25 +416,29 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
 def _bulk_straces(step, model, host, reports, rows, tune, chains, chain_idx, stat_dtypes):
     """[rows, C, D] host trace -> one NDArray per chain holding VIEWS of the bulk arrays (vectorised replacement of
     the per-draw record() of ndarray.py:258-277; no per-draw Python work, no dtype round trip)."""
-    q = np.ascontiguousarray(np.swapaxes(host["q"], 0, 1))          # [C, rows, D], engine dtype
+    q = np.swapaxes(host["q"], 0, 1)            # [C, rows, D] VIEW of the bulk trace, engine dtype (no copy)
     values = model.expand(q)
     stats = {}
     for key, dt in stat_dtypes.items():
         if key == "path_length":
             stats[key] = np.full((chains, rows), float(step.path_length))
         else:
-            stats[key] = np.ascontiguousarray(host[key].T).astype(dt, copy=False)
+            stats[key] = host[key].T.astype(dt, copy=False)
     accept_key = "mean_tree_accept" if "mean_tree_accept" in stats else "accept"
     # sampler warnings for all chains from bulk reductions; per-draw divergence records only where there are any
     div_rows = [np.nonzero(stats["diverging"][c])[0] for c in range(chains)] if stats["diverging"].any() else None
     n_post = max(0, rows - tune)
     mean_acc = stats[accept_key][:, tune:].mean(axis=1) if n_post else np.full(chains, np.nan)
+    accept_ok = step_sizes.acceptance_in_interval(mean_acc, n_post, step.target_accept)     # all chains at once
+    names, snames = list(values.keys()), list(stats.keys())
+    vals, svals = [values[n] for n in names], [stats[k] for k in snames]
     straces = []
     for c in range(chains):
-        st = NDArray.from_arrays(model, chain_idx + c, {n: v[c] for n, v in values.items()},
-                                 {k: v[c] for k, v in stats.items()})
+        st = NDArray.from_arrays(model, chain_idx + c, dict(zip(names, [v[c] for v in vals])),
+                                 dict(zip(snames, [v[c] for v in svals])))
         st._add_warnings(step._chain_warnings(reports[c], mean_acc[c], n_post,
-                                              div_rows[c] if div_rows is not None else (), stats["tune"][c]))
+                                              div_rows[c] if div_rows is not None else (), stats["tune"][c],
+                                              accept_ok=bool(accept_ok[c])))
         straces.append(st)
     return straces
 

@@ -211,7 +211,7 @@ class BaseHMC:
         warnings.extend(self.step_adapt.warnings())
         return warnings
 
-    def _chain_warnings(self, report, mean_accept_post, n_post, diverging_rows, tune_flags):
+    def _chain_warnings(self, report, mean_accept_post, n_post, diverging_rows, tune_flags, accept_ok=None):
         """Warnings of one chain of a batched run, from its device report and bulk reductions of its stats
         (`mean_accept_post`: mean acceptance statistic of the `n_post` post-tuning draws; `diverging_rows`: indices)."""
         warns = []
@@ -220,5 +220,5 @@ class BaseHMC:
             warns.append(SamplerWarning(kind, "Energy change in leapfrog step is too large.", "debug",
                                         int(i), None, None))
         warns.extend(self._divergence_summary(report.n_div_post, report.n_post))
-        warns.extend(step_sizes.acceptance_warnings(mean_accept_post, n_post, self.target_accept))
+        warns.extend(step_sizes.acceptance_warnings(mean_accept_post, n_post, self.target_accept, ok=accept_ok))
         return warns

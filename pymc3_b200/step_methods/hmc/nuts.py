@@ -56,6 +56,6 @@ class NUTS(BaseHMC):
     def warnings(self):
         return super().warnings() + self._treedepth_warning(self._samples_after_tune, self._reached_max_treedepth)
 
-    def _chain_warnings(self, report, mean_accept_post, n_post, diverging_rows, tune_flags):
-        return (super()._chain_warnings(report, mean_accept_post, n_post, diverging_rows, tune_flags)
+    def _chain_warnings(self, report, mean_accept_post, n_post, diverging_rows, tune_flags, accept_ok=None):
+        return (super()._chain_warnings(report, mean_accept_post, n_post, diverging_rows, tune_flags, accept_ok)
                 + self._treedepth_warning(report.n_post, report.n_maxdepth_post))

@@ -5,20 +5,33 @@ The recursion of pymc3/step_methods/step_sizes.py:21-58 runs inside the CUDA sta
 (`current`, `stats`, `warnings`) for one chain, fed from the device trace / chain report.
 """
 import numpy as np
-from scipy import stats
+from scipy import special
 
 from ..backends.report import SamplerWarning, WarningType
 
 
-def acceptance_warnings(mean_accept, n_draws, target):
-    """step_sizes.py:60-79: is the target inside the 95 % beta interval of the mean acceptance rate, counted over
-    (at most) 100 draws?"""
+def acceptance_in_interval(mean_accept, n_draws, target):
+    """step_sizes.py:66-70 for many chains at once: is `target` inside the central 95 % interval of
+    Beta(n_good + 1, n_bad + 1), the acceptance rate counted over (at most) 100 draws?  NaN / no draws -> True."""
+    mean_accept = np.atleast_1d(np.asarray(mean_accept, dtype="f8"))
+    ok = np.ones(mean_accept.shape, dtype=bool)
+    if not n_draws:
+        return ok
+    n_bound = min(100, int(n_draws))
+    fin = np.isfinite(mean_accept)
+    a, b = mean_accept[fin] * n_bound + 1, (1 - mean_accept[fin]) * n_bound + 1
+    lower, upper = special.betaincinv(a, b, 0.025), special.betaincinv(a, b, 0.975)
+    ok[fin] = (target >= lower) & (target <= upper)
+    return ok
+
+
+def acceptance_warnings(mean_accept, n_draws, target, ok=None):
+    """step_sizes.py:60-79: the warning when the target is outside that interval"""
     if not n_draws or not np.isfinite(mean_accept):
         return []
-    n_bound = min(100, int(n_draws))
-    n_good, n_bad = mean_accept * n_bound, (1 - mean_accept) * n_bound
-    lower, upper = stats.beta(n_good + 1, n_bad + 1).interval(0.95)
-    if target < lower or target > upper:
+    if ok is None:
+        ok = bool(acceptance_in_interval(mean_accept, n_draws, target)[0])
+    if not ok:
         msg = ("The acceptance probability does not match the target. It is %s, but should be close "
                "to %s. Try to increase the number of tuning steps." % (mean_accept, target))
         info = {"target": target, "actual": mean_accept}

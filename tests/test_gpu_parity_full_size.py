@@ -129,13 +129,16 @@ def test_wide_tcgen05_glm_at_c5_shard_size():
     model = pm.LogisticGLM(X, y)
     eng = model.engine(C, dtype="float32")
     rng = np.random.default_rng(62)
-    q = (rng.normal(size=(C, k + 1)) * 0.02 + np.concatenate([[0.3], beta.cpu().numpy()])).astype("f4")
+    # chains 0..127: positions a few posterior sds (~1.3e-3) from the generating coefficients; chains 128..255: the
+    # same positions moved by half a posterior sd -- the pairs give energy DIFFERENCES at the scale of a trajectory
+    q = (rng.normal(size=(C, k + 1)) * 0.004 + np.concatenate([[0.3], beta.cpu().numpy()])).astype("f4")
+    q[C // 2:] = q[:C // 2] + (rng.normal(size=(C // 2, k + 1)) * 6e-4).astype("f4")
     logp, grad = eng.logp_dlogp(q, glm_path=_capi.B2_GLM_TCGEN05)
     logp, grad = logp.cpu().numpy(), grad.cpu().numpy().astype("f8")
     eng.close()
     Xh, yh = X.cpu().numpy(), y.cpu().numpy()
     del X, y
-    subset = list(range(3, C, 32))
+    subset = list(range(3, C // 2, 32)) + [i + C // 2 for i in range(3, C // 2, 32)]
     l0 = np.zeros(len(subset))
     g0 = np.zeros((len(subset), k + 1))
     bounds = np.linspace(0, rows, 9).astype(int)
@@ -151,10 +154,16 @@ def test_wide_tcgen05_glm_at_c5_shard_size():
         l0[j] -= 7 * np.sum(0.5 * (-tau * b_ * b_ + np.log(tau) - np.log(2 * np.pi)))
         g0[j, 1:] -= 7 * (-tau * b_)
         assert abs(logp[i] - l0[j]) <= 1e-4 * abs(l0[j]), (i, logp[i], l0[j])
-        assert abs(logp[i] - l0[j]) < 10 * ABS_LOGP, (i, logp[i] - l0[j])      # 30x the rows of C2
+        assert abs(logp[i] - l0[j]) <= 5e-7 * abs(l0[j]), (i, logp[i] - l0[j])  # fp32-level: |logp| ~ 2e6 here
         assert _rel(grad[i], g0[j]) <= 1e-4, (i, _rel(grad[i], g0[j]))
-    print("C5 shard: max |dlogp| %.2e nats, max rel grad %.2e" % (np.abs(logp[subset] - l0).max(),
-                                                                 max(_rel(grad[i], g0[j]) for j, i in enumerate(subset))))
+    # energy differences between neighbouring positions: what a NUTS decision sees
+    half = len(subset) // 2
+    d_gpu = logp[subset[half:]] - logp[subset[:half]]
+    d_ref = l0[half:] - l0[:half]
+    assert np.abs(d_gpu - d_ref).max() < 5 * ABS_LOGP, (d_gpu - d_ref)
+    print("C5 shard: max |dlogp| %.2e nats (|logp| %.1e), max error of energy differences %.2e nats, max rel grad %.2e"
+          % (np.abs(logp[subset] - l0).max(), np.abs(l0).max(), np.abs(d_gpu - d_ref).max(),
+             max(_rel(grad[i], g0[j]) for j, i in enumerate(subset))))
 
 
 # ------------------------------------------------------------------------------- config C3
@@ -206,8 +215,10 @@ def test_leapfrog_reversible(name, dtype, rtol):
         for n_steps in (1, 2, 3, 4, 20):
             q1, p1, _ = eng.leapfrog(q0, p0, var, eps * scale, n_steps)
             q2, p2, _ = eng.leapfrog(q1, p1, var, -eps * scale, n_steps)
-            np.testing.assert_allclose(q2.cpu().numpy(), q0.astype(dtype), rtol=rtol, atol=rtol * 1e-2)
-            np.testing.assert_allclose(p2.cpu().numpy(), p0.astype(dtype), rtol=rtol, atol=rtol * 1e-2)
+            # components near zero are compared on the scale of the vector they belong to
+            for got, ref in ((q2, q0), (p2, p0)):
+                got, ref = got.cpu().numpy().astype("f8"), ref.astype(dtype).astype("f8")
+                assert np.abs(got - ref).max(axis=1).max() <= rtol * np.abs(ref).max(), (name, eps, n_steps)
     eng.close()
 
 
@@ -295,14 +306,17 @@ def test_tcgen05_lockstep_posterior_agrees_with_cpu_nuts_by_mcse_z_test():
     eng.close()
     assert 0.7 < acc < 0.92
     mean_c, sd_c, ess_c = np.array(gold["mean"]), np.array(gold["sd"]), np.array(gold["ess_bulk"])
-    ess_g = np.ravel(pm.stats.ess(q))
+    # conservative standard errors: NUTS draws are antithetic (bulk ESS above the number of draws); no credit for that
+    ess_c = np.minimum(ess_c, gold["chains"] * gold["draws"])
+    ess_g = np.minimum(np.ravel(pm.stats.ess(q)), C * draws)
     mean_g, sd_g = q.mean(axis=(0, 1)), q.reshape(-1, D).std(axis=0)
     assert float(np.ravel(pm.stats.rhat(q)).max()) < 1.02
     se_mean = np.sqrt(sd_g ** 2 / ess_g + sd_c ** 2 / ess_c)
     z = (mean_g - mean_c) / se_mean
-    assert np.abs(z).max() < 4, (int(np.abs(z).argmax()), float(np.abs(z).max()))
+    print("z(mean): mean square %.2f (1 = calibrated), max |z| %.2f at %d" % (np.mean(z ** 2), np.abs(z).max(), np.abs(z).argmax()))
+    assert np.abs(z).max() < 4, (int(np.abs(z).argmax()), float(np.abs(z).max()), float(np.mean(z ** 2)))
     # sd: se(sd) ~ sd / sqrt(2 ESS) for a near-Gaussian marginal (tail ESS is lower than bulk: use half of it)
-    se_sd = np.sqrt(sd_g ** 2 / ess_g + sd_c ** 2 / ess_c)
+    se_sd = np.sqrt(sd_g ** 2 / ess_g + sd_c ** 2 / ess_c)       # >= the asymptotic se of an sd (sd / sqrt(2 ESS))
     z_sd = (sd_g - sd_c) / se_sd
     assert np.abs(z_sd).max() < 4, (int(np.abs(z_sd).argmax()), float(np.abs(z_sd).max()))
     print("z-test tcgen05 lock-step: max |z| mean %.2f, sd %.2f; min ESS gpu %.0f cpu %.0f" %
