@@ -43,6 +43,7 @@
 #define B2_WELFORD_WIDTH 2            // the state-machine warps of the fused launch live on 136 registers
 #include "b2_engine.cuh"
 #include "b2_tc_ptx.cuh"
+#include "b2_glm_ref.cuh"
 
 #define TC_CHAINS 128                 // MMA M
 #define TC_OBS 64                     // observations per tile (GEMM1 N, GEMM2 K)
@@ -52,7 +53,8 @@
 #define TC_Y_BYTES (2 * TC_OBS * 4)                    // 512: y | y - 1/2
 #define TC_STAGE_DATA (2 * TC_XPART_BYTES + TC_Y_BYTES) // 33280 in global memory: Xhi | Xlo | y | y - 1/2
 #define TC_STAGE_BYTES (2 * TC_XPART_BYTES)            // 32768 in shared memory (y lives in its own ring)
-#define TC_MAIN_SMEM(stages) (1024 + (stages) * (TC_STAGE_BYTES + TC_Y_BYTES) + 256)
+#define TC_YS_BYTES (TC_Y_BYTES + TC_OBS * 4)          // 768 in shared memory: y | y - 1/2 | eta_ref (see TcWorkspace::eta_ref)
+#define TC_MAIN_SMEM(stages) (1024 + (stages) * (TC_STAGE_BYTES + TC_YS_BYTES) + 256)
 #define TC_EPI_GROUPS 4               // epilogue warpgroups; group g owns observation columns 16g..16g+15 of a tile
 #define TC_EPI_WARPS (4 * TC_EPI_GROUPS)
 #define TC_THREADS (128 + 32 * TC_EPI_WARPS)          // 640: the likelihood's warps
@@ -72,6 +74,14 @@ struct TcWorkspace {
     int first, count;        // the chains this workspace covers: [first, first + count)
     int post_levels;         // merge levels whose stack buffers the state-machine warps stage in shared memory
     int flush_tiles;         // the gradient accumulator is drained into the fp32 partials every flush_tiles tiles
+    // Reference-centred positions.  Q enters GEMM1 as bf16 hi + lo, i.e. to ~17 bits RELATIVE TO |q|; near the
+    // posterior mode that rounding of the position (2^-18 |q|) times the Hessian (N/4-ish) was the largest error of
+    // the gradient (2.5e-4 of a typical-set gradient at C2, round 2 parity tests).  The chains of a run sit within a
+    // few posterior sds of each other, so the GEMM works on dq = q - q_ref (q_ref = mean of the launch's live
+    // positions, refreshed at the start of every run chunk) and eta_ref = Xa . q_ref, computed once per refresh in
+    // fp64, is added back in the epilogue: the rounding is then relative to |dq|.
+    const float* q_ref;      // [TC_KP]
+    const float* eta_ref;    // [n_tiles * TC_OBS]
     int* err;                // device watchdog flag
     long long* role_clk;     // optional (B2_TC_ROLE_CLOCKS=1): {sum, count, max} cycles of the state-machine warps, then of the likelihood CTAs
     // per launch: where every chain's pending position lives
@@ -337,12 +347,16 @@ __device__ __forceinline__ float2 tc_f2(float a) { return make_float2(a, a); }
 // 16 observations of one chain row: S values -> residuals (bf16 hi | lo pairs) and this thread's logp terms.
 // ys: 16 floats of y (EPI 0) or y - 1/2 (EPI 1) in shared memory.
 template <int EPI>
-__device__ __forceinline__ float tc_epilogue16(const uint32_t (&v)[16], uint32_t ys_addr, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
-    float yv[16];
+__device__ __forceinline__ float tc_epilogue16(const uint32_t (&v)[16], uint32_t ys_addr, uint32_t ref_addr, uint32_t (&hi)[8],
+                                               uint32_t (&lo)[8]) {
+    float yv[16], rv[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)                       // ld.shared (a generic pointer here compiled to LD, not LDS)
+    for (int i = 0; i < 4; ++i) {                     // ld.shared (a generic pointer here compiled to LD, not LDS)
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(yv[4 * i]), "=f"(yv[4 * i + 1]), "=f"(yv[4 * i + 2]), "=f"(yv[4 * i + 3]) : "r"(ys_addr + 16 * i));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(rv[4 * i]), "=f"(rv[4 * i + 1]), "=f"(rv[4 * i + 2]), "=f"(rv[4 * i + 3]) : "r"(ref_addr + 16 * i));
+    }
     if (EPI == 0) {                                   // round 1: 3 MUFU per element (ex2, rcp, lg2)
         float lsum = 0.f;
 #pragma unroll
@@ -350,7 +364,7 @@ __device__ __forceinline__ float tc_epilogue16(const uint32_t (&v)[16], uint32_t
             float r2[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const float eta = __uint_as_float(v[2 * i + h]);
+                const float eta = __uint_as_float(v[2 * i + h]) + rv[2 * i + h];      // dq . x + eta_ref
                 const float yy = yv[2 * i + h];
                 const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
                 const float w1 = 1.f + e;
@@ -373,7 +387,8 @@ __device__ __forceinline__ float tc_epilogue16(const uint32_t (&v)[16], uint32_t
     float2 ls_c = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float2 eta = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        const float2 eta = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                      make_float2(rv[2 * i], rv[2 * i + 1]));           // dq . x + eta_ref
         const float2 ym = make_float2(yv[2 * i], yv[2 * i + 1]);
         const float2 t = __fmul2_rn(eta, tc_f2(1.4426950408889634f));
         const float2 e = make_float2(tc_ex2(-fabsf(t.x)), tc_ex2(-fabsf(t.y)));          // exp(-|eta|) in (0, 1]
@@ -414,7 +429,7 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* x_s = smem;
     unsigned char* y_s = x_s + STAGES * TC_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(y_s + STAGES * TC_Y_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(y_s + STAGES * TC_YS_BYTES);
     uint64_t* q_full = bars;                       // 1
     uint64_t* x_full = bars + 1;                   // STAGES
     uint64_t* x_empty = x_full + STAGES;        // STAGES
@@ -478,9 +493,10 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
                     const int s = t % STAGES;
                     if (t >= STAGES) mbar_wait(x_empty + s, ((t / STAGES) - 1) & 1, ws.err, 1);
                     const unsigned char* src = ws.xt + (size_t)(t_begin + t) * TC_STAGE_DATA;
-                    mbar_expect_tx(x_full + s, TC_STAGE_DATA);
+                    mbar_expect_tx(x_full + s, TC_STAGE_DATA + TC_OBS * 4);
                     bulk_g2s(x_s + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, x_full + s);
-                    bulk_g2s(y_s + s * TC_Y_BYTES, src + TC_STAGE_BYTES, TC_Y_BYTES, x_full + s);
+                    bulk_g2s(y_s + s * TC_YS_BYTES, src + TC_STAGE_BYTES, TC_Y_BYTES, x_full + s);
+                    bulk_g2s(y_s + s * TC_YS_BYTES + TC_Y_BYTES, ws.eta_ref + (size_t)(t_begin + t) * TC_OBS, TC_OBS * 4, x_full + s);
                 }
             }
         } else if (warp == 1) {
@@ -601,8 +617,8 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int k = 32 * cg + 2 * i;
-                const float a = (live && k < ws.K1) ? q[k] : 0.f;
-                const float b2 = (live && k + 1 < ws.K1) ? q[k + 1] : 0.f;
+                const float a = (live && k < ws.K1) ? q[k] - ws.q_ref[k] : 0.f;            // dq = q - q_ref
+                const float b2 = (live && k + 1 < ws.K1) ? q[k + 1] - ws.q_ref[k + 1] : 0.f;
                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b2);
                 const float2 back = __bfloat1622float2(h2);
                 const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - back.x, b2 - back.y);
@@ -651,7 +667,8 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
             while (k_drain < n_chunks - 1 && (k_drain + 1) * F - 1 < t) { drain(k_drain); ++k_drain; }
             const int s = t % STAGES, b = pair;
             // this warp's 32 observations of the stage's y block: y (EPI 0) or y - 1/2 (EPI 1)
-            const uint32_t ys_addr = smem_u32(y_s + s * TC_Y_BYTES) + (EPI ? TC_OBS * 4 : 0) + 128 * sub;
+            const uint32_t ys_addr = smem_u32(y_s + s * TC_YS_BYTES) + (EPI ? TC_OBS * 4 : 0) + 128 * sub;
+            const uint32_t ref_addr = smem_u32(y_s + s * TC_YS_BYTES) + TC_Y_BYTES + 128 * sub;
             const bool stamp = (lane == 0) && (sub == 0) && (wq == 0);
             if (stamp) TC_STAMP(4, t);
             mbar_wait(x_full + s, (t / STAGES) & 1, ws.err, 9);    // y values of this stage (async-proxy writes)
@@ -671,7 +688,7 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
             float lsum = 0.f;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
-                lsum += tc_epilogue16<EPI>(v[hh], ys_addr + 64 * hh, hi[hh], lo[hh]);
+                lsum += tc_epilogue16<EPI>(v[hh], ys_addr + 64 * hh, ref_addr + 64 * hh, hi[hh], lo[hh]);
             if (stamp) TC_STAMP(7, t);
             if (t >= 2) mbar_wait(p_empty + b, ((t >> 1) - 1) & 1, ws.err, 7);
             tc_fence_after();
@@ -794,11 +811,19 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     const int N = e->md.N;
     shared.n_tiles = (N + TC_OBS - 1) / TC_OBS;
     shared.n_pad_rows = shared.n_tiles * TC_OBS - N;
-    shared.flush_tiles = env_int("B2_TC_FLUSH", 32);           // 12 MMAs per tile: <= 384 truncating adds per drain
+    // drains of the gradient accumulator: off by default here (<= 87 tiles = 1044 truncating adds per slab at C2,
+    // a bias of ~3e-5 of a slab partial; each drain costs the pipeline 1-2 tile periods).  B2_TC_FLUSH=32 enables.
+    shared.flush_tiles = env_int("B2_TC_FLUSH", 1 << 20);
     if (shared.flush_tiles < 4) shared.flush_tiles = 4;
     B2_CUDA_OK(cudaMalloc(&shared.xt, (size_t)shared.n_tiles * TC_STAGE_DATA));
     B2_CUDA_OK(cudaMalloc(&shared.err, TC_ERR_INTS * sizeof(int)));
     B2_CUDA_OK(cudaMemsetAsync(shared.err, 0, TC_ERR_INTS * sizeof(int), stream));
+    float *q_ref = nullptr, *eta_ref = nullptr;
+    B2_CUDA_OK(cudaMalloc(&q_ref, TC_KP * sizeof(float)));
+    B2_CUDA_OK(cudaMalloc(&eta_ref, (size_t)shared.n_tiles * TC_OBS * sizeof(float)));
+    B2_CUDA_OK(cudaMemsetAsync(q_ref, 0, TC_KP * sizeof(float), stream));
+    B2_CUDA_OK(cudaMemsetAsync(eta_ref, 0, (size_t)shared.n_tiles * TC_OBS * sizeof(float), stream));
+    shared.q_ref = q_ref; shared.eta_ref = eta_ref;
     if (getenv("B2_TC_TIMELINE")) {
         B2_CUDA_OK(cudaMalloc(&shared.dbg, (48 * TC_DBG_TILES + 4096 * 16) * sizeof(long long)));
         B2_CUDA_OK(cudaMemsetAsync(shared.dbg, 0, (48 * TC_DBG_TILES + 4096 * 16) * sizeof(long long), stream));
@@ -856,6 +881,7 @@ void b2_glm_tc_release(b2_engine* e) {
     if (!e->glm_tc) return;
     TcHostState* hs = (TcHostState*)e->glm_tc;
     cudaFree(hs->full.dbg); cudaFree(hs->full.xt); cudaFree(hs->full.err); cudaFree(hs->full.role_clk);
+    cudaFree((void*)hs->full.q_ref); cudaFree((void*)hs->full.eta_ref);
     tc_ws_free(hs->full); tc_ws_free(hs->half[0]); tc_ws_free(hs->half[1]);
     delete hs;
     e->glm_tc = nullptr;
@@ -863,6 +889,20 @@ void b2_glm_tc_release(b2_engine* e) {
 
 static int tc_ensure(b2_engine* e, cudaStream_t stream) {
     if (!e->glm_tc) return tc_setup(e, stream);
+    return 0;
+}
+
+// q_ref = mean pending position of the chains about to be evaluated, eta_ref = Xa . q_ref (see TcWorkspace::q_ref);
+// shared by every workspace of the engine, refreshed at the start of a run chunk / before a likelihood-only launch
+static int tc_refresh_reference(b2_engine* e, const TcWorkspace& w, const float* qA, const float* qB, int ld,
+                                const B2ChainState* st, int n, cudaStream_t stream) {
+    if (env_int("B2_TC_NOREF", 0)) return 0;                  // A/B switch: positions relative to zero (round 1)
+    const int K1 = e->md.G + 1;
+    k_glm_ref_mean<<<1, TC_KP, 0, stream>>>(qA, qB, ld, st, 0, n, K1, const_cast<float*>(w.q_ref), TC_KP);
+    const int n_pad = w.n_tiles * TC_OBS;
+    k_glm_ref_eta<<<(n_pad + 7) / 8, 256, 0, stream>>>(e->md.X, e->md.N, e->md.G, w.q_ref, 1, const_cast<float*>(w.eta_ref), n_pad);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 2;
     return 0;
 }
 
@@ -888,6 +928,7 @@ int b2_glm_tc_pack(b2_engine* e, const float* qA, const float* qB, int ld, const
     int rc = tc_ensure(e, stream);
     if (rc) return rc;
     TcHostState* hs = (TcHostState*)e->glm_tc;
+    if ((rc = tc_refresh_reference(e, hs->full, qA, qB, ld, st, n, stream))) return rc;
     if (!hs->fused) return tc_compact(e, hs->full, qA, qB, ld, st, n, stream);
     for (int h = 0; h < 2; ++h) {
         if ((rc = tc_compact(e, hs->half[h], qA, qB, ld, st, hs->half[h].count, stream))) return rc;
@@ -996,6 +1037,7 @@ int b2_glm_tc_launch(b2_engine* e, const float* qA, const float* qB, float* gA, 
     if (rc) return rc;
     TcHostState* hs = (TcHostState*)e->glm_tc;
     TcWorkspace w = hs->full;                          // geometry of all C chains; n <= C points use its first tiles
+    if ((rc = tc_refresh_reference(e, w, qA, qB, ld, st, n, stream))) return rc;
     if ((rc = tc_compact(e, w, qA, qB, ld, st, n, stream))) return rc;
     w.count = n;
     TcWorkspace none;

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include "b2_engine.cuh"
 #include "b2_tc_ptx.cuh"
+#include "b2_glm_ref.cuh"
 
 #define TW_CHAINS 128
 #define TW_OBS 32
@@ -32,7 +33,8 @@
 #define TW_Y_BYTES (TW_OBS * 4)                         // 128
 #define TW_STAGE_DATA (2 * TW_XPART_BYTES + TW_Y_BYTES) // 32896 in global memory: Xhi | Xlo | y
 #define TW_STAGE_BYTES (2 * TW_XPART_BYTES)
-#define TW_SMEM_BYTES (1024 + TW_STAGES * (TW_STAGE_BYTES + TW_Y_BYTES) + 512)
+#define TW_YS_BYTES (2 * TW_Y_BYTES)                    // 256 in shared memory: y | eta_ref (b2_glm_tc.cu, TcWorkspace::q_ref)
+#define TW_SMEM_BYTES (1024 + TW_STAGES * (TW_STAGE_BYTES + TW_YS_BYTES) + 512)
 #define TW_EPI_GROUPS 4                                 // epilogue warpgroups; group g takes tiles t = g (mod 4)
 #define TW_EPI_WARPS (4 * TW_EPI_GROUPS)
 #define TW_THREADS (128 + 32 * TW_EPI_WARPS)
@@ -52,6 +54,8 @@ struct TwWorkspace {
     const float* qA; const float* qB; int ld; const B2ChainState* st; int n_chains; int K;
     int* counter;            // live chains of this launch
     int* chain_of_slot;
+    const float* q_ref;      // [1 + TW_KP] reference position (intercept first): the GEMM sees q - q_ref ...
+    const float* eta_ref;    // [n_tiles * TW_OBS] ... and the epilogue adds eta_ref = q_ref[0] + X . q_ref[1:] back
     int* x_flags;            // [0] != 0: some X element has a non-zero bf16 low part (set by the tiling kernel)
     int n_pass;              // 3 split passes, or 2 when X is bf16-representable (Xlo == 0: config C5's generator)
     int flush_tiles;         // the gradient accumulator is drained into the fp32 partials every flush_tiles tiles
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* x_s = smem;
     unsigned char* y_s = x_s + TW_STAGES * TW_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(y_s + TW_STAGES * TW_Y_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(y_s + TW_STAGES * TW_YS_BYTES);
     uint64_t* q_full = bars;                       // 1
     uint64_t* x_full = bars + 1;                   // TW_STAGES
     uint64_t* x_empty = x_full + TW_STAGES;        // TW_STAGES
@@ -189,9 +193,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
                 // Xlo == 0 (two split passes): only the hi half of the tile is read, which halves the HBM / L2
                 // traffic of a launch -- the bound when few chains are live (C5: 6.4 -> 3.2 GB per leapfrog)
                 const uint32_t x_bytes = ws.n_pass == 2 ? TW_XPART_BYTES : TW_STAGE_BYTES;
-                mbar_expect_tx(x_full + s, x_bytes + TW_Y_BYTES);
+                mbar_expect_tx(x_full + s, x_bytes + 2 * TW_Y_BYTES);
                 bulk_g2s(x_s + s * TW_STAGE_BYTES, src, x_bytes, x_full + s);
-                bulk_g2s(y_s + s * TW_Y_BYTES, src + TW_STAGE_BYTES, TW_Y_BYTES, x_full + s);
+                bulk_g2s(y_s + s * TW_YS_BYTES, src + TW_STAGE_BYTES, TW_Y_BYTES, x_full + s);
+                bulk_g2s(y_s + s * TW_YS_BYTES + TW_Y_BYTES, ws.eta_ref + (size_t)(t_begin + t) * TW_OBS, TW_Y_BYTES, x_full + s);
             }
         }
     } else if (warp == 1) {
@@ -267,15 +272,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             int sel = 0;
             if (live && ws.st) sel = ws.st[chain].sel;
             const float* q = (sel ? ws.qB : ws.qA) + (size_t)chain * ws.ld;
-            if (live) q0 = q[0];
+            if (live) q0 = q[0] - ws.q_ref[0];
 #pragma unroll
             for (int rnd = 0; rnd < 2; ++rnd) {
                 uint32_t qh[16], ql[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int k = 64 * cg + 32 * rnd + 2 * i;
-                    const float a = (live && k < ws.K) ? q[1 + k] : 0.f;
-                    const float b2 = (live && k + 1 < ws.K) ? q[2 + k] : 0.f;
+                    const float a = (live && k < ws.K) ? q[1 + k] - ws.q_ref[1 + k] : 0.f;      // dq = q - q_ref
+                    const float b2 = (live && k + 1 < ws.K) ? q[2 + k] - ws.q_ref[2 + k] : 0.f;
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b2);
                     const float2 back = __bfloat1622float2(h2);
                     const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - back.x, b2 - back.y);
@@ -319,12 +324,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             }
         };
         for (int t = cg; t < T; t += TW_EPI_GROUPS) {
-            // Before touching a tile of a new chunk, drain the chunks that end before it.  (Draining AFTER the tile
-            // instead would deadlock: storing R of tile c+3 waits for GEMM2 of tile c+1, which waits for all
-            // sixteen warps to have drained the chunk that ended at c.)
-            while (k_drain < n_chunks - 1 && (k_drain + 1) * F - 1 < t) { drain(k_drain); ++k_drain; }
             const int s = t % TW_STAGES, b = t & 1;
-            const float4* ys4 = reinterpret_cast<const float4*>(y_s + s * TW_Y_BYTES);
+            const float4* ys4 = reinterpret_cast<const float4*>(y_s + s * TW_YS_BYTES);
+            const float4* rs4 = ys4 + TW_OBS / 4;                    // eta_ref of the tile's observations
             mbar_wait(s_full + cg, (t >> 2) & 1, ws.err, 6);
             // y values of this stage: the phase is already complete (GEMM1 of this tile consumed the stage) and the
             // next one cannot complete before this tile's R is handed to GEMM2, so the parity test is unambiguous
@@ -341,18 +343,20 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             float lsum = 0.f, rsum = 0.f;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                float yv[16];
+                float yv[16], rv[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 y4 = ys4[4 * hh + i];
                     yv[4 * i] = y4.x; yv[4 * i + 1] = y4.y; yv[4 * i + 2] = y4.z; yv[4 * i + 3] = y4.w;
+                    const float4 r4 = rs4[4 * hh + i];
+                    rv[4 * i] = r4.x; rv[4 * i + 1] = r4.y; rv[4 * i + 2] = r4.z; rv[4 * i + 3] = r4.w;
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float r2[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const float eta = __uint_as_float(v[hh][2 * i + h]) + q0;
+                        const float eta = (__uint_as_float(v[hh][2 * i + h]) + q0) + rv[2 * i + h];   // dq . x + dq0 + eta_ref
                         const float yy = yv[2 * i + h];
                         const bool valid = yy >= 0.f;
                         const float e = tc_ex2(-1.4426950408889634f * fabsf(eta));     // exp(-|eta|)
@@ -373,6 +377,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
                     lo[hh][i] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
             }
+            // Chunks that ended before this tile are drained here: after this tile's math (useful work while GEMM2
+            // of the chunk's last tile finishes), but BEFORE storing its R -- that store waits for GEMM2 of tile t-2,
+            // which in a new chunk waits for all sixteen warps to have drained the old one.
+            while (k_drain < n_chunks - 1 && (k_drain + 1) * F - 1 < t) { drain(k_drain); ++k_drain; }
             if (t >= 2) mbar_wait(p_empty + ((t - 2) & 3), ((t - 2) >> 2) & 1, ws.err, 7);   // GEMM2 of tile t-2 has read R[b]
             tc_fence_after();
 #pragma unroll
@@ -384,6 +392,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_glm_tcw_main(TwWorkspace ws) 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full + cg);
+            // this warp's tile closes a chunk: drain it as soon as GEMM2 has consumed the R just stored
+            if (k_drain < n_chunks - 1 && (k_drain + 1) * F - 1 == t) { drain(k_drain); ++k_drain; }
             float ky = lsum - lp_comp, kt = lp_sum + ky;
             lp_comp = (kt - lp_sum) - ky; lp_sum = kt;
             ky = rsum - r_comp; kt = r_sum + ky;
@@ -451,7 +461,8 @@ __global__ void k_glm_tcw_finalize(TwWorkspace ws, double prior_tau, float* gA, 
 }
 
 // ---------------------------------------------------------------------------------- host
-struct TwHostState { TwWorkspace ws; };
+#define TW_REF_EVERY 256                                 // lock-step launches between two refreshes of q_ref / eta_ref
+struct TwHostState { TwWorkspace ws; long long lockstep_launches; };
 
 bool b2_glm_tcw_supported(const b2_engine* e) {
     return e->md.family == B2_FAMILY_GLM_LOGIT && e->dtype == B2_F32 && e->md.G >= 128 && e->md.G <= TW_KP && e->md.N >= 1;
@@ -475,6 +486,12 @@ static int tw_setup(b2_engine* e, cudaStream_t stream) {
     B2_CUDA_OK(cudaMalloc(&w.rpart, slabs * TW_EPI_GROUPS * TW_CHAINS * sizeof(double)));
     B2_CUDA_OK(cudaMalloc(&w.err, TC_ERR_INTS * sizeof(int)));
     B2_CUDA_OK(cudaMemsetAsync(w.err, 0, TC_ERR_INTS * sizeof(int), stream));
+    float *q_ref = nullptr, *eta_ref = nullptr;
+    B2_CUDA_OK(cudaMalloc(&q_ref, (TW_KP + 64) * sizeof(float)));
+    B2_CUDA_OK(cudaMalloc(&eta_ref, (size_t)w.n_tiles * TW_OBS * sizeof(float)));
+    B2_CUDA_OK(cudaMemsetAsync(q_ref, 0, (TW_KP + 64) * sizeof(float), stream));
+    B2_CUDA_OK(cudaMemsetAsync(eta_ref, 0, (size_t)w.n_tiles * TW_OBS * sizeof(float), stream));
+    w.q_ref = q_ref; w.eta_ref = eta_ref;
     B2_CUDA_OK(cudaMalloc(&w.x_flags, 4 * sizeof(int)));
     B2_CUDA_OK(cudaMemsetAsync(w.x_flags, 0, 4 * sizeof(int), stream));
     k_glm_tcw_prep_x<<<w.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, w.xt, w.x_flags);
@@ -497,6 +514,7 @@ void b2_glm_tcw_release(b2_engine* e) {
     TwHostState* hs = (TwHostState*)e->glm_tcw;
     cudaFree(hs->ws.xt); cudaFree(hs->ws.counter); cudaFree(hs->ws.chain_of_slot); cudaFree(hs->ws.gpart);
     cudaFree(hs->ws.lpart); cudaFree(hs->ws.rpart); cudaFree(hs->ws.err); cudaFree(hs->ws.x_flags);
+    cudaFree((void*)hs->ws.q_ref); cudaFree((void*)hs->ws.eta_ref);
     delete hs;
     e->glm_tcw = nullptr;
 }
@@ -504,8 +522,18 @@ void b2_glm_tcw_release(b2_engine* e) {
 int b2_glm_tcw_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
                       const B2ChainState* st, int n, double* logp, cudaStream_t stream) {
     if (!e->glm_tcw) { int rc = tw_setup(e, stream); if (rc) return rc; }
-    TwWorkspace& w = ((TwHostState*)e->glm_tcw)->ws;
+    TwHostState* hs = (TwHostState*)e->glm_tcw;
+    TwWorkspace& w = hs->ws;
     w.qA = qA; w.qB = qB; w.ld = ld; w.st = st; w.n_chains = n; w.K = e->md.G;
+    // reference position of this launch (b2_glm_tc.cu, TcWorkspace::q_ref).  In a lock-step run the chains move
+    // by a fraction of their spread per leapfrog, so the reference is refreshed every TW_REF_EVERY launches only.
+    if (!(getenv("B2_TC_NOREF") && atoi(getenv("B2_TC_NOREF"))) && (st == nullptr || (hs->lockstep_launches++ % TW_REF_EVERY) == 0)) {
+        k_glm_ref_mean<<<(e->md.G + 1 + 127) / 128, 128, 0, stream>>>(qA, qB, ld, st, 0, n, e->md.G + 1, const_cast<float*>(w.q_ref), TW_KP + 64);
+        const int n_pad = w.n_tiles * TW_OBS;
+        k_glm_ref_eta<<<(n_pad + 7) / 8, 256, 0, stream>>>(e->md.X, e->md.N, e->md.G, w.q_ref, 1, const_cast<float*>(w.eta_ref), n_pad);
+        B2_CUDA_OK(cudaGetLastError());
+        e->launches += 2;
+    }
     B2_CUDA_OK(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
     k_glm_tcw_compact<<<(n + 255) / 256, 256, 0, stream>>>(st, n, w.counter, w.chain_of_slot);
     B2_CUDA_OK(cudaGetLastError());
