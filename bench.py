@@ -334,6 +334,8 @@ def sample_config(ctx, args, wl, chains_total, tune, draws, split="strong", prof
         mn, _ = ctx.min_ess(ess_vec)
         res["ess"] = {"min_bulk_ess": mn, "n_scalars": int(len(ess_vec)), "over": ess_note}
         res["min_bulk_ess_per_sec"] = mn / secs[1]           # whole job incl. tuning, wall clock (benchmarks.py:163-169)
+    res["host_phases_s"] = {k: round(v, 4) for k, v in getattr(step, "_last_timing", {}).items()}
+    res["host_phases_s"]["step_and_sample_call"] = round(wall, 4)
     res["_profile"] = step._last_profile
     del trace
     return res
@@ -457,6 +459,7 @@ def run_c2_headline(ctx, args):
         e2e = {"value": r["e2e"]["value"], "unit": "grad-evals/s", "h2d_bytes_per_step": int(x_bytes // (K + W)),
                "d2h_bytes_per_step": int(d2h), "job_seconds_wall": r["job_seconds_wall"],
                "job_seconds_device": r["job_seconds_device"], "through": r["e2e"]["through"],
+               "host_phases_s": r.get("host_phases_s"),
                "note": "one pymc3_b200.sample() call for the whole job (tune + draws): X, y are uploaded once per call "
                        "(h2d per step = that upload / steps), every chunk of %d transitions is copied to the host while "
                        "the next one samples; convergence checks off (the bench computes ESS itself)" % ips}

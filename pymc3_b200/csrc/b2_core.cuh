@@ -374,14 +374,24 @@ B2_HD int b2_begin_transition(const G& g, const B2View<T>& w, int c, B2ChainStat
     T *g0 = w.V(B2_V_GE0, c), *g1 = w.V(B2_V_GE1, c), *ps = w.V(B2_V_PSUM, c);
     const bool nuts = (w.kind == B2_KIND_NUTS);
     double kin[1] = {0.0};
-    for (int i = g.lane(); i < w.D; i += G::NT) {
-        // quadpotential.py:200-203: inv_stds * normal,  inv_stds = 1 / sqrt(var)
-        const T inv_std = (T)1 / (T)sqrt(var[i]);
-        const T p = inv_std * B2Normal<T>::draw(s.key0, s.key1, t, (uint32_t)i);
-        const T qq = pq[i], gg = pg[i];
-        q1[i] = qq; p1[i] = p; g1[i] = gg;
-        if (nuts) { q0[i] = qq; p0[i] = p; g0[i] = gg; ps[i] = p; }
-        kin[0] += (double)(p * (var[i] * p));
+    // a lane draws PAIRS of components: both Box-Muller outputs of a Philox block are used (drawing them one
+    // component at a time computed every block twice; the momentum draw was 20 % of a transition end)
+    for (int j = g.lane(); 2 * j < w.D; j += G::NT) {
+        T n01[2];
+        B2Normal<T>::draw2(s.key0, s.key1, t, (uint32_t)j, n01[0], n01[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = 2 * j + h;
+            if (i < w.D) {
+                // quadpotential.py:200-203: inv_stds * normal,  inv_stds = 1 / sqrt(var)
+                const T inv_std = (T)1 / (T)sqrt(var[i]);
+                const T p = inv_std * n01[h];
+                const T qq = pq[i], gg = pg[i];
+                q1[i] = qq; p1[i] = p; g1[i] = gg;
+                if (nuts) { q0[i] = qq; p0[i] = p; g0[i] = gg; ps[i] = p; }
+                kin[0] += (double)(p * (var[i] * p));
+            }
+        }
     }
     g.allsum(kin);
     s.e0 = 0.5 * kin[0] - s.cur_logp;                     // integration.py:45-46

@@ -327,6 +327,7 @@ extern "C" int b2_engine_destroy(b2_engine* e) {
     b2_glm_tcw_release(e);
     cudaFree(e->glm_scratch); cudaFree(e->d_active); cudaFree(e->glm_ws); cudaFree(e->hier_ws);
     cudaFreeHost(e->h_active);
+    if (e->own_stream) { cudaStreamDestroy(e->own_stream); cudaEventDestroy(e->own_event); }
     if (e->ev[0]) for (int i = 0; i < 96; ++i) cudaEventDestroy(e->ev[i]);
     delete e;
     return 0;
@@ -430,7 +431,20 @@ static B2View<T> build_view(b2_engine* e, const b2_sampler_opts* o, const b2_tra
 }
 
 template <typename T>
-static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr, cudaStream_t s) {
+static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr, cudaStream_t s_in) {
+    // The run is host-synchronous (it returns when every chain has done its transitions), so it may run on a
+    // stream of its own: the caller's stream is usually the legacy default stream, which cannot be captured into a
+    // CUDA graph.  Work already queued on the caller's stream is ordered before the run through an event.
+    cudaStream_t s = s_in;
+    if (s_in == (cudaStream_t)0 || s_in == cudaStreamLegacy || s_in == cudaStreamPerThread) {
+        if (!e->own_stream) {
+            B2_CUDA_OK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+            B2_CUDA_OK(cudaEventCreateWithFlags(&e->own_event, cudaEventDisableTiming));
+        }
+        B2_CUDA_OK(cudaEventRecord(e->own_event, s_in));
+        B2_CUDA_OK(cudaStreamWaitEvent(e->own_stream, e->own_event, 0));
+        s = e->own_stream;
+    }
     B2View<T> w = build_view<T>(e, o, tr);
     int mode = o->exec_mode;
     if (mode == B2_EXEC_AUTO) mode = persistent_ok(e) ? B2_EXEC_PERSISTENT : B2_EXEC_LOCKSTEP;
@@ -476,13 +490,16 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         if (fused_tc) {
             int rc = b2_glm_tc_pack(e, (const float*)qA, (const float*)qB, e->Dp, e->st, e->C, s);
             if (rc) return rc;
+        } else if (sizeof(T) == 4 && b2_glm_tcw_supported(e) && pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05) {
+            int rc = b2_glm_tcw_refresh(e, (const float*)qA, (const float*)qB, e->Dp, e->st, e->C, s);   // reference position of this run
+            if (rc) return rc;
         }
-        for (;;) {
+        // one batch = `batch` leapfrogs of every live chain + the count of chains that still owe transitions
+        auto one_batch = [&]() -> int {
             for (int b = 0; b < batch; ++b) {
                 if (e->profile) cudaEventRecord(e->ev[3 * b], s);
                 if (fused_tc) {
-                    // likelihood + state machine of both halves (b2_glm_tc.cu); the events split the two only in
-                    // the two-kernel schedule
+                    // likelihood + state machine (b2_glm_tc.cu); the events split the two in the two-kernel schedule
                     int rc = b2_glm_tc_step(e, &w, s, e->profile ? e->ev[3 * b + 1] : (cudaEvent_t)0);
                     if (rc) return rc;
                 } else {
@@ -499,6 +516,43 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
             k_count_active<<<(e->C + 255) / 256 < 64 ? (e->C + 255) / 256 : 64, 256, 0, s>>>(e->st, e->C, w.iter_end, e->d_active);
             e->launches += 1;
             B2_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+            return 0;
+        };
+        // The batch is launch-bound at its seams (2-5 launches per leapfrog, a few us of launch latency each against
+        // 20-140 us kernels), so after a first direct batch (lazy workspace allocations happen there) it is captured
+        // into a CUDA graph and replayed.  Not on the legacy default stream (not capturable), not while per-launch
+        // events are recorded, not for the fused tensor-core schedule (its first launch differs from the rest).
+        bool use_graph = !e->profile && (cudaStream_t)s != (cudaStream_t)0 && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+                         !(getenv("B2_GRAPH") && atoi(getenv("B2_GRAPH")) == 0) && !(fused_tc && b2_glm_tc_is_fused(e));
+        cudaGraphExec_t exec = nullptr;
+        long long per_batch = 0;
+        for (int it = 0;; ++it) {
+            if (use_graph && it >= 1) {
+                if (!exec) {
+                    const long long l0 = e->launches;
+                    cudaGraph_t graph = nullptr;
+                    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                    if (ok) {
+                        const int rc = one_batch();
+                        ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && rc == 0 && graph != nullptr;
+                    }
+                    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                    if (graph) cudaGraphDestroy(graph);
+                    per_batch = e->launches - l0;
+                    e->launches = l0;
+                    if (!ok) { cudaGetLastError(); exec = nullptr; use_graph = false; }
+                }
+                if (exec) {
+                    B2_CUDA_OK(cudaGraphLaunch(exec, s));
+                    e->launches += per_batch;
+                } else {
+                    int rc = one_batch();
+                    if (rc) return rc;
+                }
+            } else {
+                int rc = one_batch();
+                if (rc) return rc;
+            }
             B2_CUDA_OK(cudaStreamSynchronize(s));
             if (e->profile) {
                 for (int b = 0; b < batch; ++b) {
@@ -509,6 +563,7 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
             }
             if (*e->h_active == 0) break;
         }
+        if (exec) cudaGraphExecDestroy(exec);
         B2_CUDA_OK(cudaGetLastError());
     }
     e->iter_done += o->n_iters;
@@ -706,6 +761,11 @@ extern "C" int b2_step_begin(b2_engine* e, const b2_sampler_opts* o, const b2_tr
     memset(&e->step_trace, 0, sizeof(e->step_trace));
     if (trace) e->step_trace = *trace;
     e->stepping = true;
+    if (e->dtype == B2_F32 && b2_glm_tcw_supported(e) && pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05) {
+        B2View<float> w0 = make_view<float>(e);
+        int rc = b2_glm_tcw_refresh(e, w0.V(B2_V_QE0, 0), w0.V(B2_V_QE1, 0), e->Dp, e->st, e->C, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     if (e->iter_done > 0) {                           // re-activate chains that finished the previous run
         cudaStream_t s = (cudaStream_t)stream;
         const int nb = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;

@@ -39,6 +39,8 @@ struct b2_engine {
     int64_t like_n;
     double adv_ms;             // advance / post kernel, same launches
     cudaEvent_t ev[96];        // per batch step b: ev[3b] | likelihood | ev[3b+1] | advance | ev[3b+2]
+    cudaStream_t own_stream;   // b2_sample_run's stream when the caller hands over the (uncapturable) default stream
+    cudaEvent_t own_event;
 };
 
 void b2_set_error(const std::string& msg);
@@ -62,6 +64,8 @@ bool b2_glm_tc_supported(const b2_engine* e);
 // wide variant (128 <= K <= 256 features, b2_glm_tcw.cu): likelihood launch only, no fused companion kernel
 bool b2_glm_tcw_supported(const b2_engine* e);
 void b2_glm_tcw_release(b2_engine* e);
+// start of a lock-step / stepwise run: reference position q_ref = mean live position, eta_ref = X . q_ref
+int b2_glm_tcw_refresh(b2_engine* e, const float* qA, const float* qB, int ld, const B2ChainState* st, int n, cudaStream_t stream);
 int b2_glm_tcw_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
                       const B2ChainState* st, int n, double* logp, cudaStream_t stream);
 void b2_glm_tc_release(b2_engine* e);

@@ -3,15 +3,18 @@
 #pragma once
 #include "b2_engine.cuh"
 
-// q_ref[k] = mean over the chains that will be evaluated (st == null: all n) of their pending position
-static __global__ void k_glm_ref_mean(const float* qA, const float* qB, int ld, const B2ChainState* st, int first, int n, int K1,
-                               float* __restrict__ q_ref, int kp) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// q_ref[k] = mean over the chains that will be evaluated (st == null: all n) of their pending position; one block
+// per feature, fixed-order tree reduction (the result must be identical on every rank of a sharded run)
+static __global__ void __launch_bounds__(256) k_glm_ref_mean(const float* qA, const float* qB, int ld, const B2ChainState* st,
+                                                             int first, int n, int K1, float* __restrict__ q_ref, int kp) {
+    __shared__ double s_sum[256];
+    __shared__ int s_cnt[256];
+    const int k = blockIdx.x;
     if (k >= kp) return;
     double acc = 0.0;
     int cnt = 0;
     if (k < K1) {
-        for (int i = 0; i < n; ++i) {
+        for (int i = threadIdx.x; i < n; i += 256) {
             const int c = first + i;
             int sel = 0;
             if (st) {
@@ -22,7 +25,13 @@ static __global__ void k_glm_ref_mean(const float* qA, const float* qB, int ld, 
             if (v - v == 0.f) { acc += (double)v; ++cnt; }           // finite positions only
         }
     }
-    q_ref[k] = cnt > 0 ? (float)(acc / cnt) : 0.f;
+    s_sum[threadIdx.x] = acc; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s_sum[threadIdx.x] += s_sum[threadIdx.x + o]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) q_ref[k] = s_cnt[0] > 0 ? (float)(s_sum[0] / s_cnt[0]) : 0.f;
 }
 
 // eta_ref[i] = q_ref[0] * has_intercept + sum_k X[i, k] q_ref[k + off]   (fp64 accumulation, one warp per row)

@@ -898,7 +898,7 @@ static int tc_refresh_reference(b2_engine* e, const TcWorkspace& w, const float*
                                 const B2ChainState* st, int n, cudaStream_t stream) {
     if (env_int("B2_TC_NOREF", 0)) return 0;                  // A/B switch: positions relative to zero (round 1)
     const int K1 = e->md.G + 1;
-    k_glm_ref_mean<<<1, TC_KP, 0, stream>>>(qA, qB, ld, st, 0, n, K1, const_cast<float*>(w.q_ref), TC_KP);
+    k_glm_ref_mean<<<TC_KP, 256, 0, stream>>>(qA, qB, ld, st, 0, n, K1, const_cast<float*>(w.q_ref), TC_KP);
     const int n_pad = w.n_tiles * TC_OBS;
     k_glm_ref_eta<<<(n_pad + 7) / 8, 256, 0, stream>>>(e->md.X, e->md.N, e->md.G, w.q_ref, 1, const_cast<float*>(w.eta_ref), n_pad);
     B2_CUDA_OK(cudaGetLastError());

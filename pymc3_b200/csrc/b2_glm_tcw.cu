@@ -461,8 +461,7 @@ __global__ void k_glm_tcw_finalize(TwWorkspace ws, double prior_tau, float* gA, 
 }
 
 // ---------------------------------------------------------------------------------- host
-#define TW_REF_EVERY 256                                 // lock-step launches between two refreshes of q_ref / eta_ref
-struct TwHostState { TwWorkspace ws; long long lockstep_launches; };
+struct TwHostState { TwWorkspace ws; };
 
 bool b2_glm_tcw_supported(const b2_engine* e) {
     return e->md.family == B2_FAMILY_GLM_LOGIT && e->dtype == B2_F32 && e->md.G >= 128 && e->md.G <= TW_KP && e->md.N >= 1;
@@ -519,20 +518,29 @@ void b2_glm_tcw_release(b2_engine* e) {
     e->glm_tcw = nullptr;
 }
 
+// Reference position (b2_glm_tc.cu, TcWorkspace::q_ref): refreshed at the start of every lock-step / stepwise run
+// (b2_engine.cu) and for every likelihood-only call -- not per leapfrog: eta_ref = X . q_ref reads the whole fp32 X.
+int b2_glm_tcw_refresh(b2_engine* e, const float* qA, const float* qB, int ld, const B2ChainState* st, int n, cudaStream_t stream) {
+    if (!e->glm_tcw) { int rc = tw_setup(e, stream); if (rc) return rc; }
+    if (getenv("B2_TC_NOREF") && atoi(getenv("B2_TC_NOREF"))) return 0;
+    TwWorkspace& w = ((TwHostState*)e->glm_tcw)->ws;
+    k_glm_ref_mean<<<TW_KP + 64, 256, 0, stream>>>(qA, qB, ld, st, 0, n, e->md.G + 1, const_cast<float*>(w.q_ref), TW_KP + 64);
+    const int n_pad = w.n_tiles * TW_OBS;
+    k_glm_ref_eta<<<(n_pad + 7) / 8, 256, 0, stream>>>(e->md.X, e->md.N, e->md.G, w.q_ref, 1, const_cast<float*>(w.eta_ref), n_pad);
+    B2_CUDA_OK(cudaGetLastError());
+    e->launches += 2;
+    return 0;
+}
+
 int b2_glm_tcw_launch(b2_engine* e, const float* qA, const float* qB, float* gA, float* gB, int ld,
                       const B2ChainState* st, int n, double* logp, cudaStream_t stream) {
     if (!e->glm_tcw) { int rc = tw_setup(e, stream); if (rc) return rc; }
     TwHostState* hs = (TwHostState*)e->glm_tcw;
     TwWorkspace& w = hs->ws;
     w.qA = qA; w.qB = qB; w.ld = ld; w.st = st; w.n_chains = n; w.K = e->md.G;
-    // reference position of this launch (b2_glm_tc.cu, TcWorkspace::q_ref).  In a lock-step run the chains move
-    // by a fraction of their spread per leapfrog, so the reference is refreshed every TW_REF_EVERY launches only.
-    if (!(getenv("B2_TC_NOREF") && atoi(getenv("B2_TC_NOREF"))) && (st == nullptr || (hs->lockstep_launches++ % TW_REF_EVERY) == 0)) {
-        k_glm_ref_mean<<<(e->md.G + 1 + 127) / 128, 128, 0, stream>>>(qA, qB, ld, st, 0, n, e->md.G + 1, const_cast<float*>(w.q_ref), TW_KP + 64);
-        const int n_pad = w.n_tiles * TW_OBS;
-        k_glm_ref_eta<<<(n_pad + 7) / 8, 256, 0, stream>>>(e->md.X, e->md.N, e->md.G, w.q_ref, 1, const_cast<float*>(w.eta_ref), n_pad);
-        B2_CUDA_OK(cudaGetLastError());
-        e->launches += 2;
+    if (st == nullptr) {                                     // likelihood-only call: the reference is this batch's mean
+        int rc = b2_glm_tcw_refresh(e, qA, qB, ld, st, n, stream);
+        if (rc) return rc;
     }
     B2_CUDA_OK(cudaMemsetAsync(w.counter, 0, sizeof(int), stream));
     k_glm_tcw_compact<<<(n + 255) / 256, 256, 0, stream>>>(st, n, w.counter, w.chain_of_slot);

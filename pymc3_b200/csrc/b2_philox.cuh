@@ -76,6 +76,16 @@ B2_HD double b2_normal(uint32_t k0, uint32_t k1, uint32_t t, uint32_t i) {
 template <typename T> struct B2Normal;
 template <> struct B2Normal<double> {
     B2_HD static double draw(uint32_t k0, uint32_t k1, uint32_t t, uint32_t i) { return b2_normal(k0, k1, t, i); }
+    // both normals of pair j (components 2j and 2j+1) from ONE Philox block and ONE Box-Muller transform
+    B2_HD static void draw2(uint32_t k0, uint32_t k1, uint32_t t, uint32_t j, double& n0, double& n1) {
+        uint32_t r[4];
+        b2_philox4x32_10(t, B2_PURPOSE_MOMENTUM, j, 0u, k0, k1, r);
+        const double u1 = 1.0 - b2_u53(r[0], r[1]);
+        const double u2 = b2_u53(r[2], r[3]);
+        const double rad = sqrt(-2.0 * log(u1));
+        const double ang = 6.283185307179586476925286766559 * u2;
+        n0 = rad * cos(ang); n1 = rad * sin(ang);
+    }
 };
 template <> struct B2Normal<float> {
     B2_HD static float draw(uint32_t k0, uint32_t k1, uint32_t t, uint32_t i) {
@@ -86,5 +96,14 @@ template <> struct B2Normal<float> {
         const float rad = sqrtf(-2.0f * logf(u1 > 1e-37f ? u1 : 1e-37f));
         const float ang = 6.2831853071795864f * u2;
         return rad * ((i & 1u) ? sinf(ang) : cosf(ang));
+    }
+    B2_HD static void draw2(uint32_t k0, uint32_t k1, uint32_t t, uint32_t j, float& n0, float& n1) {
+        uint32_t r[4];
+        b2_philox4x32_10(t, B2_PURPOSE_MOMENTUM, j, 0u, k0, k1, r);
+        const float u1 = (float)(1.0 - b2_u53(r[0], r[1]));     // (0, 1]
+        const float u2 = (float)b2_u53(r[2], r[3]);
+        const float rad = sqrtf(-2.0f * logf(u1 > 1e-37f ? u1 : 1e-37f));
+        const float ang = 6.2831853071795864f * u2;
+        n0 = rad * cosf(ang); n1 = rad * sinf(ang);
     }
 };

@@ -315,6 +315,7 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     KeyboardInterrupt (from the callback or the user) returns what is complete so far, chosen like
     sampling.py:1407-1443."""
     devices = list(devices) if devices is not None else [step.device]
+    tm = {"t0": time.perf_counter()}
     q0 = _start_array(model, start, chains)
     seeds = np.asarray(seeds, dtype=np.uint64)
     bounds = np.linspace(0, chains, len(devices) + 1).astype(int)
@@ -322,7 +323,9 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     if chunk is None:
         chunk = 1 if callback is not None else 100
     chunk = max(1, min(int(chunk), draws))
+    tm["start_array"] = time.perf_counter()
     runs = [_ShardRun(step, dev, q0[lo:hi], seeds[lo:hi], draws) for dev, lo, hi in shards]
+    tm["engines"] = time.perf_counter()
     stat_dtypes = step.stats_dtypes[0]
     interrupted = False
     done = 0
@@ -373,7 +376,9 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
                     like_ms=sum(x[0] for x in like), like_n=sum(x[1] for x in like),
                     adv_ms=sum(r.eng.profile_advance() for r in runs), shards=len(runs))
     step._last_profile = prof
+    tm["chunks"] = time.perf_counter()
     results = [r.finish() for r in runs]
+    tm["finish"] = time.perf_counter()
     rows = min(r.rows_done for r in runs) if not interrupted else done
     if len(runs) == 1:
         host = {name: arr[:rows] for name, arr in runs[0].host.items()}
@@ -394,6 +399,9 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
                 raise SamplingError("Bad initial energy (chain %d)" % (chain_idx + c)) from err
 
     straces = _bulk_straces(step, model, host, reports, rows, tune, chains, chain_idx, stat_dtypes)
+    tm["straces"] = time.perf_counter()
+    keys = ["start_array", "engines", "chunks", "finish", "straces"]
+    step._last_timing = {k: tm[k] - tm[p] for k, p in zip(keys, ["t0"] + keys[:-1])}      # seconds per host phase
     if interrupted:
         straces, length = _choose_chains(straces, tune)
         return MultiTrace(straces)[:length]
