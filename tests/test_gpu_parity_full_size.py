@@ -53,7 +53,8 @@ def test_tcgen05_glm_at_c2_size_all_chains_live():
     warm-up) with the absolute bound, and far-off ones (|eta| up to ~10 and ~40, early warm-up / saturated
     sigmoids) where the tensor core's truncating fp32 accumulation (a relative bias of ~2e-7 on eta, towards zero)
     times sum_i (y_i - sigmoid_i) eta_i ~ 3e4 .. 2e5 shows as 0.01 .. 0.08 nats: bounded there at 3x the absolute
-    bound or 5e-7 |logp| (fp32-level), whichever is larger."""
+    bound or 2e-6 |logp| (fp32-level: 1e5 terms of size ~2 summed in fp32 tiles), whichever is larger -- energy
+    differences at that distance from the mode are hundreds of nats."""
     from oracle import densities as od
     from pymc3_b200 import model as pm
     X, y = _c2()
@@ -73,7 +74,7 @@ def test_tcgen05_glm_at_c2_size_all_chains_live():
         for i in range(5, C, 64):
             l0, g0 = oracle(q[i].astype("f8"))
             assert abs(logp[i] - l0) <= 1e-4 * abs(l0), (name, i, logp[i], l0)
-            assert abs(logp[i] - l0) < max(bound, 5e-7 * abs(l0)), (name, i, logp[i] - l0)     # far cases: fp32-level relative
+            assert abs(logp[i] - l0) < max(bound, 2e-6 * abs(l0)), (name, i, logp[i] - l0)     # far cases: fp32-level relative
             assert _rel(grad[i], g0) <= 1e-4, (name, i, _rel(grad[i], g0))
             worst, worst_g = max(worst, abs(logp[i] - l0)), max(worst_g, _rel(grad[i], g0))
         print("C2 logp_dlogp %-9s: max |dlogp| %.2e nats, max rel dlogp error %.2e" % (name, worst, worst_g))
