@@ -108,7 +108,22 @@ class SamplerReport:
         target.extend(warnings)
 
     def _log_summary(self):
-        for warn in self._warnings:
+        """report.py:205-207 logs every warning; with thousands of chains the same kind of warning repeats per
+        chain, so beyond 8 chains each kind is logged once with the number of chains it concerns."""
+        if len(self._chain_warnings) <= 8:
+            for warn in self._warnings:
+                logger.log(_LEVELS[warn.level], warn.message)
+            return
+        by_kind = {}
+        for chain, warns in self._chain_warnings.items():
+            for warn in warns:
+                if _LEVELS[warn.level] <= logging.DEBUG:
+                    continue
+                entry = by_kind.setdefault((warn.kind, warn.level), [set(), warn.message])
+                entry[0].add(chain)
+        for (kind, level), (chains_hit, example) in by_kind.items():
+            logger.log(_LEVELS[level], "%s  [%d of %d chains]" % (example, len(chains_hit), len(self._chain_warnings)))
+        for warn in self._global_warnings:
             logger.log(_LEVELS[warn.level], warn.message)
 
     def _slice(self, start, stop, step):

@@ -216,7 +216,8 @@ class _ShardRun:
         self.copy_stream = torch.cuda.Stream(device=self.eng.dev)
         self.rows_done = 0
         self.device_seconds = 0.0
-        self.chunk_log = []                   # (rows done, wall clock, device seconds so far) after every chunk
+        self.chunk_log = []                   # (rows done, wall clock, device seconds, leapfrogs so far) after every chunk
+        self.log_grads = bool(getattr(step, "_log_chunk_grads", False))
         self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         self._jobs = queue.Queue()
         self._error = None
@@ -277,7 +278,8 @@ class _ShardRun:
             self._ev[1].synchronize()
             self.device_seconds += self._ev[0].elapsed_time(self._ev[1]) / 1e3
         self.rows_done = hi
-        self.chunk_log.append((hi, time.perf_counter(), self.device_seconds))
+        n_grad = sum(rep.n_grad for rep in self.eng.reports()) if self.log_grads else 0
+        self.chunk_log.append((hi, time.perf_counter(), self.device_seconds, n_grad))
         return lo, hi
 
     def flush(self):
@@ -391,7 +393,7 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     step._last_kernel_launches = sum(r[2] for r in results)
     step._last_reports = reports
     step._last_device_seconds = max(r.device_seconds for r in runs)
-    step._last_chunk_log = [(rows_, t_ - tm["t0"], d_) for rows_, t_, d_ in runs[0].chunk_log]
+    step._last_chunk_log = [(rows_, t_ - tm["t0"], d_, g_) for rows_, t_, d_, g_ in runs[0].chunk_log]
     step._last_n_grad = int(sum(rep.n_grad for rep in reports))
 
     for c, rep in enumerate(reports):
