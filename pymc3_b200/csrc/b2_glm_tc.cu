@@ -330,7 +330,11 @@ __device__ __forceinline__ void tc_post_role(const TcWorkspace& ws, const B2View
 }
 
 // bar.sync over the likelihood's 640 threads only (the state-machine warps of a fused launch never join it)
+#ifdef TC_V_SYNCTHREADS                               // timing variant (two-kernel build only)
+__device__ __forceinline__ void tc_main_sync() { __syncthreads(); }
+#else
 __device__ __forceinline__ void tc_main_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); }
+#endif
 
 // degree-7 fit of log1p(e) / e on [0, 1] (Chebyshev nodes; |error| of e * P(e) in fp32 Horner form < 2.4e-7,
 // the same as lg2.approx's): coefficients of e^0 .. e^7
@@ -354,8 +358,12 @@ __device__ __forceinline__ float tc_epilogue16(const uint32_t (&v)[16], uint32_t
     for (int i = 0; i < 4; ++i) {                     // ld.shared (a generic pointer here compiled to LD, not LDS)
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(yv[4 * i]), "=f"(yv[4 * i + 1]), "=f"(yv[4 * i + 2]), "=f"(yv[4 * i + 3]) : "r"(ys_addr + 16 * i));
+#ifdef TC_V_NOETA                                     // timing variant: no reference (round 1's epilogue inputs)
+        rv[4 * i] = rv[4 * i + 1] = rv[4 * i + 2] = rv[4 * i + 3] = 0.f;
+#else
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(rv[4 * i]), "=f"(rv[4 * i + 1]), "=f"(rv[4 * i + 2]), "=f"(rv[4 * i + 3]) : "r"(ref_addr + 16 * i));
+#endif
     }
     if (EPI == 0) {                                   // round 1: 3 MUFU per element (ex2, rcp, lg2)
         float lsum = 0.f;
@@ -751,7 +759,8 @@ struct TcHostState {
     TcWorkspace half[2];       // fused lock-step: chains [0, h) | [h, C), one likelihood launch each per leapfrog
     bool pending[2];           // half's likelihood has run, its state machine has not consumed the partials yet
     bool fused;                // B2_TC_FUSED (default 0)
-    int epi;                   // B2_TC_EPI   (default 1)
+    int epi;                   // B2_TC_EPI   (default 0)
+    int stages_unfused;        // X ring depth of the two-kernel build: 5 (default), 4 or 6 (B2_TC_STAGES_UNFUSED)
     int stages_fused;          // X ring depth of the fused kernel (5, or 4 when the state-machine warps need the room)
     int post_levels;
 };
@@ -836,7 +845,14 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     // state-machine warps' shuffles and shared-memory accesses queue behind the epilogue's MUFU / TMEM traffic in the
     // SM's MIO pipe and a transition end takes 150-185 k cycles instead of ~50 k stand-alone.
     hs->fused = env_int("B2_TC_FUSED", 0) != 0 && !shared.dbg;      // the timeline tools read the two-kernel step
-    hs->epi = env_int("B2_TC_EPI", 1) != 0 ? 1 : 0;
+    // Defaults from round 2's A/B runs on one box (profiles/README.md): (1) the packed-fp32 / polynomial epilogue
+    // (EPI 1) takes a third of the MUFU work away but is 1 % SLOWER in the lock-step job (FMA pipe 28 -> 41 %);
+    // (2) a 6-stage ring plus the y / y - 1/2 / eta_ref rows needs 197.75 KB, which tips the launch from the 196 KB
+    // into the 228 KB shared-memory carve-out (L1 60 -> 28 KB) and costs 5 % (122.5 -> 128.7 us per launch, the same
+    // with a 5-stage ring padded to that size); 5 stages fit the 196 KB carve-out.
+    hs->epi = env_int("B2_TC_EPI", 0) != 0 ? 1 : 0;
+    const int su = env_int("B2_TC_STAGES_UNFUSED", 5);
+    hs->stages_unfused = su == 6 ? 6 : (su == 4 ? 4 : 5);
     // shared memory of the fused launch: X ring + the four state-machine warps (hot slots + staged merge levels);
     // prefer the deeper ring, stage as many merge levels as still fit
     hs->stages_fused = env_int("B2_TC_STAGES", 5) <= 4 ? 4 : 5;
@@ -867,6 +883,10 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     const size_t fs = tc_fused_smem(hs, e->Dp);
     if ((rc = tc_main_attr<6, 0, false>(TC_MAIN_SMEM(6)))) return rc;
     if ((rc = tc_main_attr<6, 1, false>(TC_MAIN_SMEM(6)))) return rc;
+    if ((rc = tc_main_attr<4, 0, false>(TC_MAIN_SMEM(4)))) return rc;
+    if ((rc = tc_main_attr<4, 1, false>(TC_MAIN_SMEM(4)))) return rc;
+    if ((rc = tc_main_attr<5, 0, false>(TC_MAIN_SMEM(6)))) return rc;
+    if ((rc = tc_main_attr<5, 1, false>(TC_MAIN_SMEM(6)))) return rc;
     if ((rc = tc_main_attr<5, 0, true>(fs))) return rc;
     if ((rc = tc_main_attr<5, 1, true>(fs))) return rc;
     if ((rc = tc_main_attr<4, 0, true>(fs))) return rc;
@@ -951,7 +971,15 @@ static int tc_launch(b2_engine* e, const TcHostState* hs, const TcWorkspace& ws,
     if (grid <= 0) return 0;
     const double tau = e->md.hp[0];
     if (!FUSED) {
-        if (hs->epi) k_glm_tc_main<6, 1, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
+        if (hs->stages_unfused == 5) {
+            smem = TC_MAIN_SMEM(5) + (size_t)env_int("B2_TC_SMEM_PAD", 0);      // experiment: push the launch into the 228 KB carve-out
+            if (hs->epi) k_glm_tc_main<5, 1, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
+            else k_glm_tc_main<5, 0, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
+        } else if (hs->stages_unfused == 4) {
+            smem = TC_MAIN_SMEM(4);
+            if (hs->epi) k_glm_tc_main<4, 1, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
+            else k_glm_tc_main<4, 0, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
+        } else if (hs->epi) k_glm_tc_main<6, 1, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
         else k_glm_tc_main<6, 0, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
     } else if (hs->stages_fused == 5) {
         if (hs->epi) k_glm_tc_main<5, 1, true><<<grid, TC_THREADS_FUSED, smem, stream>>>(ws, wsp, v, tau);
