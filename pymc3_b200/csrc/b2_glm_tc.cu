@@ -760,7 +760,7 @@ struct TcHostState {
     bool pending[2];           // half's likelihood has run, its state machine has not consumed the partials yet
     bool fused;                // B2_TC_FUSED (default 0)
     int epi;                   // B2_TC_EPI   (default 0)
-    int stages_unfused;        // X ring depth of the two-kernel build: 5 (default), 4 or 6 (B2_TC_STAGES_UNFUSED)
+    int stages_unfused;        // X ring depth of the two-kernel build: 4 (default), 5 or 6 (B2_TC_STAGES_UNFUSED)
     int stages_fused;          // X ring depth of the fused kernel (5, or 4 when the state-machine warps need the room)
     int post_levels;
 };
@@ -849,9 +849,10 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     // (EPI 1) takes a third of the MUFU work away but is 1 % SLOWER in the lock-step job (FMA pipe 28 -> 41 %);
     // (2) a 6-stage ring plus the y / y - 1/2 / eta_ref rows needs 197.75 KB, which tips the launch from the 196 KB
     // into the 228 KB shared-memory carve-out (L1 60 -> 28 KB) and costs 5 % (122.5 -> 128.7 us per launch, the same
-    // with a 5-stage ring padded to that size); 5 stages fit the 196 KB carve-out.
+    // with a 5-stage ring padded to that size); 5 stages fit the 196 KB carve-out (123.1 us), 4 stages the 164 KB
+    // one (121.1 us) -- the ring is deep enough for L2-resident tiles either way, so 4 it is.
     hs->epi = env_int("B2_TC_EPI", 0) != 0 ? 1 : 0;
-    const int su = env_int("B2_TC_STAGES_UNFUSED", 5);
+    const int su = env_int("B2_TC_STAGES_UNFUSED", 4);
     hs->stages_unfused = su == 6 ? 6 : (su == 4 ? 4 : 5);
     // shared memory of the fused launch: X ring + the four state-machine warps (hot slots + staged merge levels);
     // prefer the deeper ring, stage as many merge levels as still fit
