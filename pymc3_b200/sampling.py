@@ -91,7 +91,7 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
             start = start_
     elif kwargs:
         raise ValueError("Unknown arguments to `sample`: %s" % sorted(kwargs))   # :132-134
-    if not getattr(step, "_batched", False):
+    if not hasattr(step, "_host_driven"):
         raise NotImplementedError("pymc3_b200.sample runs NUTS / HamiltonianMC step methods only")
     if start is None:
         start = [model.test_point] * chains
@@ -105,8 +105,13 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
         start = [{k: v for k, v in trace.point(-1, chain=c).items() if k in model.free_RVs} for c in trace.chains]
 
     t_start = time.time()
-    mtrace = _sample_batched(step, model, draws, tune, chains, start, random_seed, devices, chain_idx,
-                             callback=callback, chunk=chunk)
+    if getattr(step, "_batched", False):
+        mtrace = _sample_batched(step, model, draws, tune, chains, start, random_seed, devices, chain_idx,
+                                 callback=callback, chunk=chunk)
+    else:
+        # a user potential / step_rand: chains one after the other, draws one at a time through step.step(),
+        # like the reference's _sample_many -> _iter_sample (sampling.py:786-936)
+        mtrace = _sample_sequential(step, model, draws, tune, chains, start, random_seed, chain_idx, callback)
     t_sampling = time.time() - t_start
 
     discard = tune if discard_tuned_samples else 0
@@ -471,6 +476,37 @@ def _chunk_callbacks(callback, step, model, runs, shards, lo, hi, draws, tune, c
                 point = {k: v[i] for k, v in values.items()}
                 row = {k: v[i] for k, v in stats.items()}
                 callback(trace=st, draw=Draw(chain_idx + c_lo + c, i == draws - 1, i, i < tune, [row], point, None))
+
+
+def _sample_sequential(step, model, draws, tune, chains, start, seeds, chain_idx, callback):
+    """sampling.py:641-690, 847-936 for step methods that are driven from the host (user potentials)."""
+    straces = []
+    try:
+        for c in range(chains):
+            np.random.seed(int(seeds[c]) % (2 ** 32))
+            point = dict(model.test_point)
+            point.update({k: v for k, v in start[c].items() if k in point})
+            strace = NDArray(model=model)
+            strace.setup(draws, chain_idx + c, step.stats_dtypes)
+            straces.append(strace)
+            step.tune = bool(tune)
+            step.iter_count = 0
+            for i in range(draws):
+                if i == tune:
+                    step.stop_tuning()
+                point, stats = step.step(point)
+                strace.record(point, stats)
+                if callback is not None:
+                    warns = step.warnings() if i == draws - 1 else None
+                    callback(trace=strace, draw=Draw(chain_idx + c, i == draws - 1, i, i < tune, stats, point, warns))
+            strace.close()
+            strace._add_warnings(step.warnings())
+    except KeyboardInterrupt:
+        for st in straces:
+            st.close()
+        straces, length = _choose_chains(straces, tune)
+        return MultiTrace(straces)[:length]
+    return MultiTrace(straces)
 
 
 def iter_sample(draws, step, start=None, trace=None, chain=0, tune=None, model=None, random_seed=None,

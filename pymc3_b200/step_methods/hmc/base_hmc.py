@@ -16,7 +16,7 @@ from ...backends.report import SamplerWarning, WarningType
 from ...exceptions import SamplingError
 from ...model import modelcontext
 from .. import step_sizes
-from .quadpotential import QuadPotentialDiagAdapt, quad_potential
+from .quadpotential import QuadPotentialDiag, QuadPotentialDiagAdapt, quad_potential
 
 logger = logging.getLogger("pymc3")
 
@@ -40,7 +40,6 @@ class BaseHMC:
 
     default_blocked = True
     generates_stats = True
-    _batched = True            # can run all chains in one device engine (sampling.sample)
     _kind = None
 
     def __init__(self, vars=None, scaling=None, step_scale=0.25, is_cov=False, model=None, blocked=True,
@@ -78,12 +77,16 @@ class BaseHMC:
         if scaling is not None and potential is not None:
             raise ValueError("Can not specify both potential and scaling.")
         self.potential = potential if potential is not None else quad_potential(scaling, is_cov)
-        if getattr(self.potential, "device_kind", None) not in ("diag", "diag_adapt"):
-            raise NotImplementedError("only QuadPotentialDiag / QuadPotentialDiagAdapt run on the device; "
-                                      "got %r" % type(self.potential).__name__)
+        # The built-in diagonal potentials are run by the device state machine.  Anything else that speaks the
+        # QuadPotential protocol (a user subclass overriding velocity / energy / random / update, test_quadpotential.py:
+        # 138-155; a custom step_rand callable) is honoured by driving the tree from the host and calling the user's
+        # object per leapfrog, with logp / dlogp still evaluated on the device (host_transition.py).
+        self._host_driven = type(self.potential) not in (QuadPotentialDiag, QuadPotentialDiagAdapt)
+        if self._host_driven and not all(hasattr(self.potential, m) for m in ("velocity", "energy", "random")):
+            raise TypeError("potential must implement the QuadPotential protocol (velocity, energy, random); "
+                            "got %r" % type(self.potential).__name__)
         if step_rand is not None and not getattr(step_rand, "_b2_unif", False):
-            raise NotImplementedError("custom step_rand callables cannot run on the device; "
-                                      "use the built-in jitter (HamiltonianMC default) or None")
+            self._host_driven = True
         self._step_rand = step_rand
         self._exec_mode = {"auto": _capi.B2_EXEC_AUTO, "persistent": _capi.B2_EXEC_PERSISTENT,
                            "lockstep": _capi.B2_EXEC_LOCKSTEP}[exec_mode]
@@ -138,8 +141,49 @@ class BaseHMC:
         q, stats = self.astep(q0)
         return self._model.array_to_dict(q), stats
 
+    @property
+    def _batched(self):
+        """can sampling.sample() run all chains of this step method in one device engine?"""
+        return not self._host_driven
+
+    def _host_astep(self, q0):
+        """base_hmc.py:133-199 for a user potential: one transition on the host (host_transition.py)."""
+        from . import host_transition as ht
+        integ = ht.HostIntegrator(self.potential, lambda q: self._logp_dlogp_func(np.asarray(q, dtype="f8")))
+        p0 = np.asarray(self.potential.random(), dtype="f8")
+        start = integ.start(q0, p0)
+        if not np.isfinite(start.energy):
+            self.potential.raise_ok(self._ordering.vmap)
+            self._warnings.append(SamplerWarning(WarningType.BAD_ENERGY, "Bad initial energy, check any log probabilities "
+                                                 "that are inf or -inf, nan or very small", "critical", self.iter_count, None, None))
+            raise SamplingError("Bad initial energy")
+        adapt = self.tune and self.adapt_step_size
+        step_size = float(self.step_adapt.current(adapt))
+        self.step_size = step_size
+        if self._step_rand is not None:
+            step_size = float(self._step_rand(step_size))
+        if self._kind == _capi.B2_NUTS:
+            depth = self.early_max_treedepth if (self.tune and self.iter_count < 200) else self.max_treedepth
+            q, grad, stats = ht.nuts_transition(integ, start, step_size, depth, float(self.Emax))
+            accept = stats["mean_tree_accept"]
+            if not self.tune and stats["depth"] >= depth and not stats["diverging"]:
+                self._reached_max_treedepth += 1
+        else:
+            q, grad, stats = ht.hmc_transition(integ, start, step_size, float(self.path_length), int(self.max_steps), float(self.Emax))
+            accept = stats["accept"]
+        self.step_adapt.update(accept, adapt)
+        self.potential.update(q, grad, self.tune)
+        stats["tune"] = bool(self.tune)
+        stats.update(self.step_adapt.stats())
+        it = self.iter_count
+        row = {k: np.dtype(dt).type(stats[k]) for k, dt in self.stats_dtypes[0].items()}
+        self._account(row, it)
+        return np.asarray(q, dtype="f8"), [row]
+
     def astep(self, q0):
         q0 = np.asarray(q0, dtype="f8")
+        if self._host_driven:
+            return self._host_astep(q0)
         if self._engine is None:
             self._engine = self._make_engine(1)
             seed = np.random.randint(2 ** 30)          # the reference draws from the global stream

@@ -6,12 +6,15 @@ pseudo-sample weight / window); the arithmetic -- v = var (.) p, p ~ N(0,1)/sqrt
 Welford windows of QuadPotentialDiagAdapt (:211-225, :313-353) -- runs per chain on the device
 (csrc/b2_core.cuh).  The small NumPy methods below keep the object usable stand-alone, as the
 reference's unit tests use it (tests/test_quadpotential.py:48-135); the sampler never calls them.
-Dense potentials (QuadPotentialFull*, :400-572) are a "next" row.
+Dense potentials (QuadPotentialFull / QuadPotentialFullInv, :400-470) are host objects: a step
+method that holds one is driven from the host (host_transition.py) -- a [D, D] matrix-vector product per leapfrog on
+the host, logp / dlogp on the device.  They are not part of the chain-batched device path.
 """
 import numpy as np
+import scipy.linalg
 
-__all__ = ["quad_potential", "QuadPotentialDiag", "QuadPotentialDiagAdapt", "isquadpotential",
-           "PositiveDefiniteError"]
+__all__ = ["quad_potential", "QuadPotentialDiag", "QuadPotentialDiagAdapt", "QuadPotentialFull",
+           "QuadPotentialFullInv", "isquadpotential", "PositiveDefiniteError"]
 
 
 class PositiveDefiniteError(ValueError):
@@ -36,8 +39,7 @@ def quad_potential(C, is_cov):
     partial_check_positive_definite(C)
     if C.ndim == 1:
         return QuadPotentialDiag(C if is_cov else 1.0 / C)
-    raise NotImplementedError("dense mass matrices (QuadPotentialFull/FullInv) are not on the device "
-                              "path yet; pass a 1-d scaling")
+    return QuadPotentialFull(C) if is_cov else QuadPotentialFullInv(C)
 
 
 class QuadPotential:
@@ -135,6 +137,32 @@ class QuadPotentialDiagAdapt(_DiagMath):
     def reset(self):
         self._var = self._initial_diag.astype(self.dtype).copy()
         self._stds = np.sqrt(self._var)
+        # host-side Welford windows: used only when a user SUBCLASS of this potential drives host transitions
+        # (quadpotential.py:211-225, 313-353); the batched path keeps these windows on the device
+        self._fg = [self._initial_weight, self._initial_mean.copy(), self._initial_diag * self._initial_weight]
+        self._bg = [0.0, np.zeros(self._n), np.zeros(self._n)]
+        self._n_samples = 0
+
+    @staticmethod
+    def _welford_add(win, x):
+        win[0] += 1.0
+        old = x - win[1]
+        win[1] = win[1] + old / win[0]
+        win[2] = win[2] + old * (x - win[1])
+
+    def update(self, sample, grad, tune):
+        if not tune:
+            return
+        x = np.asarray(sample, dtype="f8")
+        window = self.adaptation_window
+        self._welford_add(self._fg, x)
+        self._welford_add(self._bg, x)
+        self._var = (self._fg[2] / self._fg[0]).astype(self.dtype)
+        self._stds = np.sqrt(self._var)
+        if self._n_samples > 0 and self._n_samples % window == 0:
+            self._fg = self._bg
+            self._bg = [0.0, np.zeros(self._n), np.zeros(self._n)]
+        self._n_samples += 1
 
     def device_init(self):
         return dict(mean=self._initial_mean, var=self._initial_diag, weight=self._initial_weight,
@@ -158,3 +186,51 @@ class QuadPotentialDiagAdapt(_DiagMath):
             for ii in np.where(bad)[0]:
                 lines.append("The derivative of RV `{}`.ravel()[{}] is {}.".format(names[ii][0], names[ii][1], tail))
             raise ValueError("\n".join(lines))
+
+
+class _DenseMath(QuadPotential):
+    """energy and velocity_energy in terms of velocity (quadpotential.py:425-436, 463-472)"""
+
+    def energy(self, x, velocity=None):
+        if velocity is None:
+            velocity = self.velocity(x)
+        return 0.5 * np.dot(x, velocity)
+
+    def velocity_energy(self, x, v_out):
+        self.velocity(x, out=v_out)
+        return 0.5 * np.dot(x, v_out)
+
+
+class QuadPotentialFull(_DenseMath):
+    """Dense potential given the covariance (quadpotential.py:438-472): v = cov p, p ~ chol^-T z."""
+
+    def __init__(self, cov, dtype=None):
+        self.dtype = np.dtype(dtype or "float64")
+        self._cov = np.array(cov, dtype=self.dtype, copy=True)
+        self._chol = scipy.linalg.cholesky(self._cov, lower=True)
+        self._n = len(self._cov)
+
+    def velocity(self, x, out=None):
+        return np.dot(self._cov, x, out=out)
+
+    def random(self):
+        z = np.random.normal(size=self._n).astype(self.dtype)
+        return scipy.linalg.solve_triangular(self._chol.T, z, overwrite_b=True)
+
+
+class QuadPotentialFullInv(_DenseMath):
+    """Dense potential given the precision A (quadpotential.py:400-436): v = A^-1 p via Cholesky, p = L z."""
+
+    def __init__(self, A, dtype=None):
+        self.dtype = np.dtype(dtype or "float64")
+        self.L = scipy.linalg.cholesky(np.asarray(A, dtype=self.dtype), lower=True)
+
+    def velocity(self, x, out=None):
+        vel = scipy.linalg.cho_solve((self.L, True), x)
+        if out is None:
+            return vel
+        out[:] = vel
+        return out
+
+    def random(self):
+        return np.dot(self.L, np.random.normal(size=self.L.shape[0]).astype(self.dtype))

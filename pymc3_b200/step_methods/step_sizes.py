@@ -46,10 +46,25 @@ class DualAverageAdaptation:
         self._gamma, self._k, self._t0 = gamma, k, t0
         self._log_step = np.log(initial_step)
         self._log_bar = self._log_step
+        self._hbar, self._count, self._mu = 0.0, 1, np.log(10 * initial_step)
         self._tuned_stats = []
 
     def current(self, tune):
         return np.exp(self._log_step) if tune else np.exp(self._log_bar)
+
+    def update(self, accept_stat, tune):
+        """step_sizes.py:40-52 on the host -- used only by host-driven transitions (user potentials); the batched
+        path runs the same recursion on the device (b2_core.cuh, b2_end_transition)."""
+        if not tune:
+            self._tuned_stats.append(float(accept_stat))
+            return
+        count, k, t0, gamma = self._count, self._k, self._t0, self._gamma
+        w = 1.0 / (count + t0)
+        self._hbar = (1 - w) * self._hbar + w * (self._target - accept_stat)
+        self._log_step = self._mu - self._hbar * np.sqrt(count) / gamma
+        mk = count ** -k
+        self._log_bar = mk * self._log_step + (1 - mk) * self._log_bar
+        self._count += 1
 
     def sync(self, step_size, step_size_bar, post_tune_accept):
         """Adopt the device state after a run."""

@@ -221,3 +221,30 @@ def test_diagnostics():
     assert pm.rhat(y + np.arange(4)[:, None] * 3) > 1.5            # chains stuck at different places
     assert abs(pm.stats.mcse_mean(x)[0] - 1 / np.sqrt(4000)) < 0.004
     assert pm.stats.bfmi(rng.normal(size=(2, 500))).shape == (2,)
+
+
+def test_host_driven_transitions_sample_the_target():
+    """pymc3_b200/step_methods/hmc/host_transition.py (the path of user potentials) on a NumPy density: stationary
+    standard deviations of a diagonal normal, NUTS and HMC, dense and diagonal potentials."""
+    from pymc3_b200.step_methods.hmc import host_transition as ht
+    from pymc3_b200.step_methods.hmc.quadpotential import QuadPotentialDiag, QuadPotentialFull
+    sig = np.array([1.0, 2.0, 0.5])
+
+    def f(q):
+        return -0.5 * np.sum((q / sig) ** 2), -q / sig ** 2
+
+    np.random.seed(4)
+    for pot in (QuadPotentialDiag(np.ones(3)), QuadPotentialFull(np.diag(sig ** 2) + 0.05)):
+        integ = ht.HostIntegrator(pot, f)
+        q, draws, acc = np.zeros(3), [], []
+        for _ in range(3000):
+            q, _, st = ht.nuts_transition(integ, integ.start(q, pot.random()), 0.35, 10, 1000.0)
+            draws.append(q)
+            acc.append(st["mean_tree_accept"])
+        assert np.allclose(np.std(draws, axis=0), sig, rtol=0.1) and 0.6 < np.mean(acc) <= 1.0
+    integ = ht.HostIntegrator(QuadPotentialDiag(np.ones(3)), f)
+    q, draws = np.zeros(3), []
+    for _ in range(3000):
+        q, _, st = ht.hmc_transition(integ, integ.start(q, integ.pot.random()), 0.3, 2.0, 1024, 1000.0)
+        draws.append(q)
+    assert np.allclose(np.std(draws, axis=0), sig, rtol=0.1)

@@ -278,3 +278,53 @@ def test_device_diagnostics_match_host_diagnostics_on_a_real_trace():
     np.testing.assert_allclose(rhat_d.cpu().numpy(), pm.stats.rhat(host), rtol=1e-9)
     assert float(rhat_d.max()) < 1.05 and float(ess_d.min()) > 1000
     eng.close()
+
+
+def test_user_potential_is_called():
+    """pymc3/tests/test_quadpotential.py:138-155: a user subclass of QuadPotentialDiag passed as potential= must have
+    its methods called while sampling (host-driven transitions, logp / dlogp on the device)."""
+    from pymc3_b200.step_methods.hmc import quadpotential
+    called = []
+
+    class Potential(quadpotential.QuadPotentialDiag):
+        def energy(self, x, velocity=None):
+            called.append(1)
+            return super().energy(x, velocity)
+
+    with pm.StdNormal(1):
+        step = pm.NUTS(potential=Potential(np.ones(1)), dtype="float64")
+        trace = pm.sample(10, init=None, step=step, chains=1, tune=10, compute_convergence_checks=False)
+    assert called and len(trace) == 10
+    assert set(trace.stat_names) >= {"depth", "tree_size", "mean_tree_accept", "energy", "diverging", "step_size"}
+
+
+def test_dense_mass_matrix_through_host_driven_transitions():
+    """test_step.py:534-565 in spirit: NUTS with a dense `scaling=C` (QuadPotentialFull, quadpotential.py:438-472)
+    reproduces the moments of the target."""
+    sig = np.array([1.0, 2.0, 0.5])
+    with pm.StdNormal(3, sigma=sig):
+        C = np.diag(sig ** 2) + 0.05
+        step = pm.NUTS(scaling=C, is_cov=True, dtype="float64")
+        assert type(step.potential).__name__ == "QuadPotentialFull" and not step._batched
+        trace = pm.sample(600, tune=300, chains=2, step=step, random_seed=11, compute_convergence_checks=False)
+    x = trace["x"]
+    assert np.abs(x.mean(axis=0)).max() < 0.25 and np.allclose(x.std(axis=0), sig, rtol=0.15)
+
+
+def test_sample_callback_and_cancel():
+    """pymc3/tests/test_sampling.py:194-219: the callback sees every draw; KeyboardInterrupt from it returns the
+    draws made so far."""
+    seen = []
+    with pm.StdNormal(2):
+        pm.sample(10, tune=0, chains=2, step=pm.NUTS(), random_seed=3, compute_convergence_checks=False,
+                  callback=lambda trace, draw: seen.append((draw.chain, draw.draw_idx, len(trace))))
+    assert len(seen) == 20 and all(n == i + 1 for _, i, n in seen)
+
+    def cancel(trace, draw):
+        if len(trace) >= 5:
+            raise KeyboardInterrupt()
+
+    with pm.StdNormal(2):
+        trace = pm.sample(10, tune=0, chains=1, step=pm.NUTS(), random_seed=3, callback=cancel,
+                          compute_convergence_checks=False)
+    assert len(trace) == 5
