@@ -283,7 +283,7 @@ def start_dicts(model, chains, first_chain):
     return out
 
 
-def sample_config(ctx, args, wl, chains_total, tune, draws, split="strong", profile_chunks=0, chunk=100):
+def sample_config(ctx, args, wl, chains_total, tune, draws, split="strong", profile_chunks=0, chunk=100, run_ahead=True):
     """One complete NUTS job through the PUBLIC API (pymc3_b200.sample) on this rank's share of the chains.
     Returns the per-config result object (rank 0) -- value from the CUDA-event time of the sampling launches inside
     the call, e2e from the wall clock around the whole call (model upload, sampling, trace download, MultiTrace)."""
@@ -305,7 +305,7 @@ def sample_config(ctx, args, wl, chains_total, tune, draws, split="strong", prof
         step._profile_last_chunks = profile_chunks
         step._log_chunk_grads = True          # leapfrog counters after every chunk (for e2e over the timed steps)
         trace = pm.sample(draws, tune=tune, chains=chains, step=step, start=starts, random_seed=seeds, chunk=chunk,
-                          discard_tuned_samples=False, compute_convergence_checks=False, progressbar=False)
+                          run_ahead=run_ahead, discard_tuned_samples=False, compute_convergence_checks=False, progressbar=False)
     torch.cuda.synchronize(ctx.dev)
     wall = time.perf_counter() - t0
     ctx.barrier()
@@ -461,7 +461,7 @@ def run_c2_headline(ctx, args):
     # ---- e2e: the same job through the call a user makes
     e2e = None
     if not args.skip_e2e:
-        r = sample_config(ctx, args, wl, chains, tune, total - tune, split="weak", chunk=ips)
+        r = sample_config(ctx, args, wl, chains, tune, total - tune, split="weak", chunk=ips, run_ahead=ahead)
         x_bytes = sum(t.numel() * t.element_size() for t in [torch.as_tensor(model.X), torch.as_tensor(model.y)])
         d2h = (chains * ndim * 4 + chains * (7 * 8 + 2 * 4 + 2)) * ips          # one step's rows of q + 11 stats
         # Like `value`, the headline e2e number is over the K timed steps (the W warm-up steps, early tuning with its

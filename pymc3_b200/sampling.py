@@ -42,14 +42,15 @@ def _cpu_count():
 def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=None, chain_idx=0,
            chains=None, cores=None, tune=500, progressbar=True, model=None, random_seed=None,
            discard_tuned_samples=True, compute_convergence_checks=True, callback=None, devices=None,
-           chunk=None, **kwargs):
+           chunk=None, run_ahead=True, **kwargs):
     """Draw samples from the posterior using the given step method (sampling.py:230).
 
     `cores` is accepted for signature compatibility; chain parallelism is the GPU's.
     `devices`: CUDA device indices to shard chains over (default: the step's device).
     `callback(trace, draw)` is called for every chain and draw (sampling.py:1396-1398) after each chunk of `chunk`
     transitions (default: 1 with a callback, else 100); raising KeyboardInterrupt in it, or pressing Ctrl-C,
-    returns the draws completed so far (sampling.py:1407-1409).
+    returns the draws completed so far (sampling.py:1407-1409).  `run_ahead=False` makes every chain stop at every
+    chunk boundary instead of running ahead into the next chunk's rows (per-chunk accounting in bench.py).
     Extra keyword arguments configure the auto-assigned NUTS sampler (sampling.py:439-451).
     """
     model = modelcontext(model)
@@ -107,7 +108,7 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
     t_start = time.time()
     if getattr(step, "_batched", False):
         mtrace = _sample_batched(step, model, draws, tune, chains, start, random_seed, devices, chain_idx,
-                                 callback=callback, chunk=chunk)
+                                 callback=callback, chunk=chunk, run_ahead=run_ahead)
     else:
         # a user potential / step_rand: chains one after the other, draws one at a time through step.step(),
         # like the reference's _sample_many -> _iter_sample (sampling.py:786-936)
@@ -239,6 +240,8 @@ class _ShardRun:
                         for name, t in self.trace.items()} for _ in range(2)]
             events = [None, None]
             spans = [None, None]
+            for arr in self.host.values():        # first touch of the (lazily mapped) host arrays happens here, not
+                arr.fill(0)                       # on the critical path of the last copies
 
             def drain(k):
                 if events[k] is not None:
@@ -314,7 +317,7 @@ def _np_dtype(t):
 
 
 def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, chain_idx=0, callback=None,
-                    chunk=None):
+                    chunk=None, run_ahead=True):
     """All chains in one engine per device; chains are split contiguously over devices.
 
     The job runs in chunks of `chunk` transitions (default 100; 1 when a `callback` is given, so that it sees
@@ -342,12 +345,12 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     def run_all(n):
         errors = []
         if len(runs) == 1:
-            runs[0].run_chunk(n, tune, True)
+            runs[0].run_chunk(n, tune, run_ahead)
             return
 
         def work(r):
             try:
-                r.run_chunk(n, tune, True)
+                r.run_chunk(n, tune, run_ahead)
             except BaseException as err:      # surfaced on the caller's thread
                 errors.append(err)
         threads = [threading.Thread(target=work, args=(r,)) for r in runs]

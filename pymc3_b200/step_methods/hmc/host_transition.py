@@ -119,8 +119,9 @@ def nuts_transition(integ, start, step_size, max_depth, emax):
         turned = _turning(p_sum, first1, last2) or _turning(sum1 + first2.p, first1, first2) or \
             _turning(last1.p + sum2, last1, last2)                    # :298-307
     accept = 0.0
-    if log_size > 0:
-        accept = float(np.exp(log_accept - (log_size + np.log1p(-np.exp(-log_size)))))       # nuts.py:391-397, log space
+    if log_size > 0:                                                 # nuts.py:391-397: exp(log_accept) / expm1(log_size), in log space
+        log_den = log_size + np.log1p(-np.exp(-log_size)) if log_size > 30 else np.log(np.expm1(log_size))
+        accept = float(np.exp(log_accept - log_den))
     q, grad, energy, logp = prop
     stats = {"depth": depth, "mean_tree_accept": accept, "energy_error": energy - e0, "energy": energy,
              "tree_size": float(n_prop), "max_energy_error": max_de, "model_logp": logp, "diverging": bool(diverged)}

@@ -248,3 +248,30 @@ def test_host_driven_transitions_sample_the_target():
         q, _, st = ht.hmc_transition(integ, integ.start(q, integ.pot.random()), 0.3, 2.0, 1024, 1000.0)
         draws.append(q)
     assert np.allclose(np.std(draws, axis=0), sig, rtol=0.1)
+
+
+def test_sample_with_a_dense_potential_runs_host_driven_chains():
+    """sample() with a step method that is driven from the host (dense scaling -> QuadPotentialFull): sequential
+    chains, per-draw record, sampler stats; the density here is a NumPy stand-in for the device ValueGradFunction."""
+    sig = np.array([1.0, 2.0, 0.5])
+
+    class FakeVG:
+        size, dtype = 3, np.dtype("f8")
+
+        def __call__(self, q, grad_out=None):
+            return np.array(-0.5 * np.sum((q / sig) ** 2)), -q / sig ** 2
+
+    class Model(pm.StdNormal):
+        def logp_dlogp_function(self, *a, **k):
+            return FakeVG()
+
+    seen = []
+    with Model(3, sigma=sig):
+        step = pm.NUTS(scaling=np.diag(sig ** 2) + 0.05, is_cov=True, dtype="float64")
+        assert type(step.potential).__name__ == "QuadPotentialFull" and not step._batched
+        trace = pm.sample(400, tune=200, chains=2, step=step, random_seed=11, compute_convergence_checks=False,
+                          callback=lambda trace, draw: seen.append(draw.draw_idx))
+    x = trace["x"]
+    assert x.shape == (800, 3) and np.allclose(x.std(axis=0), sig, rtol=0.2) and np.abs(x.mean(axis=0)).max() < 0.4
+    assert len(seen) == 2 * 600 and 0.6 < trace.get_sampler_stats("mean_tree_accept").mean() < 0.99
+    assert np.isfinite(trace.get_sampler_stats("step_size")).all()
