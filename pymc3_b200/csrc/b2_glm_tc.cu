@@ -40,7 +40,8 @@
 #include <cuda_bf16.h>
 #include <cstring>
 #include <cstdlib>
-#define B2_WELFORD_WIDTH 2            // the state-machine warps of the fused launch live on 136 registers
+// (the fused launch's state-machine warps would want B2_WELFORD_WIDTH 2 to stay near their 80 registers; the fused
+//  schedule is off by default, so the stand-alone state-machine kernel keeps the 4-wide mass-matrix update)
 #include "b2_engine.cuh"
 #include "b2_tc_ptx.cuh"
 #include "b2_glm_ref.cuh"
@@ -853,7 +854,7 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     // one (121.1 us) -- the ring is deep enough for L2-resident tiles either way, so 4 it is.
     hs->epi = env_int("B2_TC_EPI", 0) != 0 ? 1 : 0;
     const int su = env_int("B2_TC_STAGES_UNFUSED", 4);
-    hs->stages_unfused = su == 6 ? 6 : (su == 4 ? 4 : 5);
+    hs->stages_unfused = (su >= 3 && su <= 6) ? su : 4;
     // shared memory of the fused launch: X ring + the four state-machine warps (hot slots + staged merge levels);
     // prefer the deeper ring, stage as many merge levels as still fit
     hs->stages_fused = env_int("B2_TC_STAGES", 5) <= 4 ? 4 : 5;
@@ -884,6 +885,8 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     const size_t fs = tc_fused_smem(hs, e->Dp);
     if ((rc = tc_main_attr<6, 0, false>(TC_MAIN_SMEM(6)))) return rc;
     if ((rc = tc_main_attr<6, 1, false>(TC_MAIN_SMEM(6)))) return rc;
+    if ((rc = tc_main_attr<3, 0, false>(TC_MAIN_SMEM(3)))) return rc;
+    if ((rc = tc_main_attr<3, 1, false>(TC_MAIN_SMEM(3)))) return rc;
     if ((rc = tc_main_attr<4, 0, false>(TC_MAIN_SMEM(4)))) return rc;
     if ((rc = tc_main_attr<4, 1, false>(TC_MAIN_SMEM(4)))) return rc;
     if ((rc = tc_main_attr<5, 0, false>(TC_MAIN_SMEM(6)))) return rc;
@@ -976,6 +979,10 @@ static int tc_launch(b2_engine* e, const TcHostState* hs, const TcWorkspace& ws,
             smem = TC_MAIN_SMEM(5) + (size_t)env_int("B2_TC_SMEM_PAD", 0);      // experiment: push the launch into the 228 KB carve-out
             if (hs->epi) k_glm_tc_main<5, 1, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
             else k_glm_tc_main<5, 0, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
+        } else if (hs->stages_unfused == 3) {
+            smem = TC_MAIN_SMEM(3);
+            if (hs->epi) k_glm_tc_main<3, 1, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
+            else k_glm_tc_main<3, 0, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
         } else if (hs->stages_unfused == 4) {
             smem = TC_MAIN_SMEM(4);
             if (hs->epi) k_glm_tc_main<4, 1, false><<<grid, TC_THREADS, smem, stream>>>(ws, wsp, v, tau);
