@@ -338,6 +338,7 @@ def sample_config(ctx, args, wl, chains_total, tune, draws, split="strong", prof
     res["chunk_log"] = getattr(step, "_last_chunk_log", None)       # (rows done, seconds since the call began, device seconds)
     res["host_phases_s"] = {k: round(v, 4) for k, v in getattr(step, "_last_timing", {}).items()}
     res["host_phases_s"]["step_and_sample_call"] = round(wall, 4)
+    res["host_phases_s"]["finish_detail"] = {k: round(v, 4) for k, v in (getattr(step, "_last_finish_phases", None) or {}).items()}
     res["_profile"] = step._last_profile
     del trace
     return res
@@ -479,6 +480,7 @@ def run_c2_headline(ctx, args):
                "d2h_bytes_per_step": int(d2h), "job_seconds_wall": r["job_seconds_wall"],
                "job_seconds_device": r["job_seconds_device"], "through": r["e2e"]["through"],
                "host_phases_s": r.get("host_phases_s"),
+               "chunk_log": [[int(a), round(b, 4), round(c, 4), int(d)] for a, b, c, d in log],
                "note": "value = the K timed steps of one pymc3_b200.sample() call for the whole job (whole_call_value includes the "
                        "warm-up steps): X, y are uploaded once per call "
                        "(h2d per step = that upload / steps), every chunk of %d transitions is copied to the host while "

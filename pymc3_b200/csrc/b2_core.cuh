@@ -40,9 +40,11 @@ enum { B2_FAIL_NONE = 0, B2_FAIL_BAD_INITIAL_ENERGY = 1 };
 // vector slots in the per-engine state buffer, each [n_chains][Dp]
 enum {
     B2_V_QE0 = 0, B2_V_QE1, B2_V_PE0, B2_V_PE1, B2_V_GE0, B2_V_GE1,   // left / right edge (q, p, grad)
-    B2_V_POLD, B2_V_PSUM, B2_V_PROPQ, B2_V_PROPG, B2_V_VAR,
+    B2_V_VAR,                                                          // the 7 slots above are touched by EVERY leapfrog,
+    B2_V_POLD, B2_V_PSUM, B2_V_PROPQ, B2_V_PROPG,                      // these four once per tree doubling / transition
     B2_V_STACK0,                                                       // then 5 per stack buffer
 };
+#define B2_V_EVERY_LEAPFROG (B2_V_VAR + 1)
 enum { B2_S_PFIRST = 0, B2_S_PLAST, B2_S_PSUM, B2_S_Q, B2_S_G, B2_S_NVEC };
 #define B2_NUM_VEC_SLOTS (B2_V_STACK0 + B2_S_NVEC * B2_MAX_LEVELS)
 
@@ -99,11 +101,13 @@ struct B2View {
     int *tr_depth, *tr_tree_size, *tr_n_steps;
     unsigned char *tr_diverging, *tr_tune, *tr_accepted;
 
-    // Optional on-chip copy of THIS chain's hot slots (edges, p_old, p_sum, proposal, var):
-    // [B2_V_STACK0][Dp], staged in shared memory by the kernel for the duration of one launch.
+    // Optional on-chip copy of THIS chain's first `hot_slots` vector slots (all 11: edges, var, p_old, p_sum,
+    // proposal; or only the B2_V_EVERY_LEAPFROG first): [hot_slots][Dp], staged in shared memory by the kernel
+    // for the duration of one launch.
     T* hot;
+    int hot_slots;
     B2_HD T* V(int slot, int c) const {
-        if (hot && slot < B2_V_STACK0) return hot + (size_t)slot * Dp;
+        if (hot && slot < hot_slots) return hot + (size_t)slot * Dp;
         return vec + ((size_t)slot * C + c) * Dp;
     }
     B2_HD T* Vglobal(int slot, int c) const { return vec + ((size_t)slot * C + c) * Dp; }
@@ -579,9 +583,13 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
         const int buf = b2_map_get(s.slot_map, 0);
         T *sf = w.S(buf, B2_S_PFIRST, c), *sl = w.S(buf, B2_S_PLAST, c), *ss = w.S(buf, B2_S_PSUM, c);
         T *sq = w.S(buf, B2_S_Q, c), *sg = w.S(buf, B2_S_G, c);
+        // A one-leaf sub-tree has p_first = p_last = p_sum.  Only the depth-0 doubling reads all three back (top merge);
+        // otherwise the next leaf's merge takes p_first for all of them and writes p_last / p_sum itself.
+        const bool solo = (s.depth == 0);
         for (int i = g.lane(); i < w.D; i += G::NT) {
             const T p = pe[i];
-            sf[i] = p; sl[i] = p; ss[i] = p; sq[i] = qe[i]; sg[i] = ge[i];
+            sf[i] = p; sq[i] = qe[i]; sg[i] = ge[i];
+            if (solo) { sl[i] = p; ss[i] = p; }
         }
         w.LV(c, 0, buf) = leaf_ls; w.LV(c, 1, buf) = leaf_la;
         w.LV(c, 2, buf) = energy; w.LV(c, 3, buf) = logp_new;
@@ -600,7 +608,8 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const double en2 = leaf2 ? energy : w.LV(c, 2, b2i);
             const double lp2 = leaf2 ? logp_new : w.LV(c, 3, b2i);
             T *f1 = w.S(b1, B2_S_PFIRST, c), *l1 = w.S(b1, B2_S_PLAST, c), *s1 = w.S(b1, B2_S_PSUM, c);
-            const bool turning = b2_uturn<T, G>(g, w.D, var, f1, l1, s1, f2, l2, s2, k > 0, s1, l1);
+            // k == 0: t1 is the single leaf stored one step ago (p_first stands for its p_last and p_sum)
+            const bool turning = b2_uturn<T, G>(g, w.D, var, f1, leaf2 ? f1 : l1, leaf2 ? f1 : s1, f2, l2, s2, k > 0, s1, l1);
             if (turning) { s.turned = 1; break; }
             const double ls1 = w.LV(c, 0, b1);
             const double la1 = w.LV(c, 1, b1);

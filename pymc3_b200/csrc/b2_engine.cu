@@ -100,15 +100,15 @@ __global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w, int 
     if (g.lane() == 0) w.st[c] = s;
 }
 
-// hot != null: shared memory for this chain's B2_V_STACK0 hot vector slots (B2View::hot), loaded once,
+// hot != null: shared memory for this chain's first w.hot_slots vector slots (B2View::hot), loaded once,
 // written back when the chain's run ends -- the persistent kernel then touches HBM/L2 only for the stack
-// buffers, the Welford windows and the trace.
+// buffers, the Welford windows, the trace and (hot_slots == B2_V_EVERY_LEAPFROG) the once-per-doubling slots.
 template <typename T, typename G>
 __device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const B2ModelData& m, int c, T* hot) {
     B2ChainState s = w.st[c];
     if (s.phase == B2_PHASE_FAILED || (s.phase == B2_PHASE_DONE && s.iter >= w.iter_cap)) return;
     if (hot) {
-        for (int slot = 0; slot < B2_V_STACK0; ++slot) {
+        for (int slot = 0; slot < w.hot_slots; ++slot) {
             const T* src = w.Vglobal(slot, c);
             T* dst = hot + (size_t)slot * w.Dp;
             for (int i = g.lane(); i < w.Dp; i += G::NT) dst[i] = src[i];
@@ -131,7 +131,7 @@ __device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const 
     }
     if (hot) {
         g.sync();
-        for (int slot = 0; slot < B2_V_STACK0; ++slot) {
+        for (int slot = 0; slot < w.hot_slots; ++slot) {
             T* dst = w.Vglobal(slot, c);
             const T* src = hot + (size_t)slot * w.Dp;
             for (int i = g.lane(); i < w.Dp; i += G::NT) dst[i] = src[i];
@@ -149,10 +149,11 @@ __global__ void k_persistent_warp(B2View<T> w, B2ModelData m, int hot_elems) {
     persistent_body<T, B2WarpGroup>(g, w, m, c, hot_elems ? reinterpret_cast<T*>(hot_raw) + (size_t)(threadIdx.x >> 5) * hot_elems : (T*)0);
 }
 
-// NT threads own one chain.  With the hot slots in shared memory only one block fits an SM at D ~ 3000, so the
-// block itself has to bring enough warps to hide latency: NT is picked per run (persistent_block_threads).
-template <typename T, int NT>
-__global__ void __launch_bounds__(NT) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems) {
+// NT threads own one chain.  At D ~ 3000 all 11 hot slots take 128 KB of shared memory (fp32): one block per SM,
+// which then has to bring enough warps itself (NT = 512).  With only the 7 every-leapfrog slots on chip (82 KB) two
+// blocks share an SM (CTAS = 2): the barriers and L2 round trips of one chain's step are filled by the other chain.
+template <typename T, int NT, int CTAS>
+__global__ void __launch_bounds__(NT, CTAS) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems) {
     extern __shared__ __align__(16) unsigned char hot_raw[];
     __shared__ double red[8 * (NT / 32)];
     B2BlockGroup<NT> g;
@@ -160,18 +161,18 @@ __global__ void __launch_bounds__(NT) k_persistent_block(B2View<T> w, B2ModelDat
     persistent_body<T, B2BlockGroup<NT>>(g, w, m, blockIdx.x, hot_elems ? reinterpret_cast<T*>(hot_raw) : (T*)0);
 }
 
-template <typename T, int NT>
+template <typename T, int NT, int CTAS>
 static int launch_persistent_block(b2_engine* e, const B2View<T>& w, int hot_elems, size_t hot_bytes, cudaStream_t s) {
     if (hot_bytes > 48 * 1024)
-        B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_block<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
-    k_persistent_block<T, NT><<<e->C, NT, hot_bytes, s>>>(w, e->md, hot_elems);
+        B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_block<T, NT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
+    k_persistent_block<T, NT, CTAS><<<e->C, NT, hot_bytes, s>>>(w, e->md, hot_elems);
     return 0;
 }
 
-static int persistent_block_threads(const b2_engine* e) {
-    const char* env = getenv("B2_PBLOCK_NT");
-    if (env) { const int v = atoi(env); if (v == 256 || v == 512 || v == 1024) return v; }
-    return e->D >= 2048 ? 512 : 256;
+static int env_choice(const char* name, int dflt, int a, int b, int c) {
+    const char* env = getenv(name);
+    if (env) { const int v = atoi(env); if (v == a || v == b || v == c) return v; }
+    return dflt;
 }
 
 // chains that still owe transitions of this call (with run-ahead, faster chains are already past iter_end)
@@ -192,6 +193,7 @@ static B2View<T> make_view(b2_engine* e) {
     memset(&w, 0, sizeof(w));
     w.C = e->C; w.D = e->D; w.Dp = e->Dp;
     w.vec = (T*)e->vec; w.wv_mean = e->wv_mean; w.wv_m2 = e->wv_m2; w.st = e->st; w.lv = e->lv; w.logp_eval = e->logp_eval;
+    w.hot_slots = B2_V_STACK0;
     return w;
 }
 
@@ -456,16 +458,32 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
     const int nb_warp = (e->C + B2_WARPS_PER_BLOCK - 1) / B2_WARPS_PER_BLOCK;
     if (mode == B2_EXEC_PERSISTENT) {
         // shared-memory residency of each chain's hot vector slots when it fits (11 * Dp elements per chain)
-        int hot_elems = B2_V_STACK0 * e->Dp;
+        // Block per chain: two blocks per SM when two sets of the 7 every-leapfrog slots fit next to each other
+        // (B2_PBLOCK_CTAS / _NT / _HOT override the choice for A/B runs).
+        const size_t slot_bytes = (size_t)e->Dp * sizeof(T);
+        const size_t smem_sm = (size_t)227 * 1024;
+        int ctas = 1, nt = e->D >= 2048 ? 512 : 256;
+        if (blk) {
+            if (2 * (B2_V_EVERY_LEAPFROG * slot_bytes + 4096) <= smem_sm && 2 * (B2_V_STACK0 * slot_bytes + 4096) > smem_sm) { ctas = 2; nt = 256; }
+            ctas = env_choice("B2_PBLOCK_CTAS", ctas, 1, 2, 2);
+            nt = env_choice("B2_PBLOCK_NT", nt, 256, 512, 1024);
+            if (ctas == 2 && nt == 1024) nt = 512;
+            w.hot_slots = env_choice("B2_PBLOCK_HOT", ctas == 2 ? B2_V_EVERY_LEAPFROG : B2_V_STACK0, B2_V_EVERY_LEAPFROG, B2_V_STACK0, B2_V_STACK0);
+        }
+        int hot_elems = w.hot_slots * e->Dp;
         size_t hot_bytes = (size_t)hot_elems * sizeof(T) * (blk ? 1 : B2_WARPS_PER_BLOCK);
+        if (hot_bytes > (size_t)200 * 1024 && blk && w.hot_slots == B2_V_STACK0) {       // fp64 at D ~ 3000: the 7 still fit
+            w.hot_slots = B2_V_EVERY_LEAPFROG; hot_elems = w.hot_slots * e->Dp; hot_bytes = (size_t)hot_elems * sizeof(T);
+        }
         if (hot_bytes > (size_t)200 * 1024) { hot_elems = 0; hot_bytes = 0; }
         if (hot_bytes > 48 * 1024 && !blk)
             B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
         if (blk) {
-            const int nt = persistent_block_threads(e);
-            int rc = nt == 1024 ? launch_persistent_block<T, 1024>(e, w, hot_elems, hot_bytes, s)
-                   : nt == 512  ? launch_persistent_block<T, 512>(e, w, hot_elems, hot_bytes, s)
-                                : launch_persistent_block<T, 256>(e, w, hot_elems, hot_bytes, s);
+            int rc = ctas == 2 ? (nt == 512 ? launch_persistent_block<T, 512, 2>(e, w, hot_elems, hot_bytes, s)
+                                            : launch_persistent_block<T, 256, 2>(e, w, hot_elems, hot_bytes, s))
+                   : nt == 1024 ? launch_persistent_block<T, 1024, 1>(e, w, hot_elems, hot_bytes, s)
+                   : nt == 512  ? launch_persistent_block<T, 512, 1>(e, w, hot_elems, hot_bytes, s)
+                                : launch_persistent_block<T, 256, 1>(e, w, hot_elems, hot_bytes, s);
             if (rc) return rc;
         }
         else k_persistent_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, hot_bytes, s>>>(w, e->md, hot_elems);

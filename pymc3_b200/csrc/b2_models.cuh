@@ -227,16 +227,31 @@ B2_HD double b2_eval_stoch_vol(const G& g, const B2ModelData& m, const T* q, T* 
         part[2] += -(T)0.5 * l1 + hnu1_over_nu * zr;
         grad[1 + i] = gv + (nu1_t * zr - (T)1);
     }
-    double acc[3] = {(double)part[0], (double)part[1], (double)part[2]};
+    // The terms that depend on (a, c) only -- two lgamma, two digamma, the logs of the hyper-parameters: ~1000 fp64
+    // instructions -- were evaluated by every thread of the group on the critical path of every leapfrog.  Each is now
+    // one job done by one lane of a different warp (a one-warp or one-lane group does them all), and the group sum
+    // below delivers the totals to everybody.
+    double acc[5] = {(double)part[0], (double)part[1], (double)part[2], 0.0, 0.0};
+    {
+        constexpr int NW = (G::NT + 31) / 32;
+        const int wid = g.lane() >> 5;
+        if ((g.lane() & 31) == 0) {
+            if (0 % NW == wid) acc[3] += Tn * lgamma(hnu1);
+            if (1 % NW == wid) acc[3] -= Tn * lgamma(0.5 * nu);
+            if (2 % NW == wid) acc[4] += Tn * 0.5 * b2_digamma(hnu1);
+            if (3 % NW == wid) acc[4] -= Tn * 0.5 * b2_digamma(0.5 * nu);
+            if (4 % NW == wid) acc[3] += log(m.hp[0]) + log(m.hp[1]);
+        }
+    }
     g.allsum(acc);
     const double n1 = (double)(Tn - 1);
-    double lp = (log(m.hp[0]) - m.hp[0] * s + a)                                  // Exp(s|10) + jacobian
+    double lp = (-m.hp[0] * s + a)                                                // Exp(s|10) + jacobian   (log lam in acc[3])
               + (-0.5 * inv_s2 * acc[1] + n1 * (-a - 0.5 * B2_LOG_2PI))            // GRW innovations (init Flat)
-              + (log(m.hp[1]) - m.hp[1] * nu + c)                                  // Exp(nu|0.1) + jacobian
-              + acc[0] + Tn * (lgamma(hnu1) - lgamma(0.5 * nu) - 0.5 * log(nu) - 0.5 * B2_LOG_PI);
+              + (-m.hp[1] * nu + c)                                                // Exp(nu|0.1) + jacobian
+              + acc[0] + acc[3] + Tn * (-0.5 * c - 0.5 * B2_LOG_PI);               // log(nu) = c
     if (g.lane() == 0) {
         grad[0] = (T)(-m.hp[0] * s + 1.0 + acc[1] * inv_s2 - n1);
-        const double dnu = Tn * (0.5 * b2_digamma(hnu1) - 0.5 * b2_digamma(0.5 * nu) - 0.5 / nu) + acc[2];
+        const double dnu = acc[4] - Tn * 0.5 / nu + acc[2];
         grad[1 + Tn] = (T)(-m.hp[1] * nu + 1.0 + nu * dnu);
     }
     return lp;

@@ -300,13 +300,17 @@ class _ShardRun:
         self._thread.start()
 
     def finish(self):
+        t0 = time.perf_counter()
         self._jobs.put(None)
         self._thread.join()
         if self._error is not None:
             raise self._error
+        t1 = time.perf_counter()
         out = (self.eng.reports(), self.eng.mass_var(), self.eng.kernel_launches())
+        t2 = time.perf_counter()
         self.eng.close()
         self.trace = None
+        self.finish_phases = {"copies": t1 - t0, "reports": t2 - t1, "release": time.perf_counter() - t2}
         return out
 
 
@@ -403,6 +407,7 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     step._last_device_seconds = max(r.device_seconds for r in runs)
     step._last_chunk_log = [(rows_, t_ - tm["t0"], d_, g_) for rows_, t_, d_, g_ in runs[0].chunk_log]
     step._last_n_grad = int(sum(rep.n_grad for rep in reports))
+    step._last_finish_phases = runs[0].finish_phases
 
     for c, rep in enumerate(reports):
         if rep.phase == _capi.PHASE_FAILED:
