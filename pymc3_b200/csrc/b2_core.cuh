@@ -108,9 +108,10 @@ struct B2View {
     int hot_slots;
     B2_HD T* V(int slot, int c) const {
         if (hot && slot < hot_slots) return hot + (size_t)slot * Dp;
-        return vec + ((size_t)slot * C + c) * Dp;
+        return Vglobal(slot, c);
     }
-    B2_HD T* Vglobal(int slot, int c) const { return vec + ((size_t)slot * C + c) * Dp; }
+    // (slot stride and the chain's offset are loop invariants of every kernel: one multiply-add per call is left)
+    B2_HD T* Vglobal(int slot, int c) const { return vec + (size_t)c * Dp + (size_t)slot * ((size_t)C * Dp); }
     double* lv_hot;               // optional shared-memory copy of this chain's [4][B2_MAX_LEVELS] scalars
     B2_HD double& LV(int c, int which, int buf) const {
         if (lv_hot) return lv_hot[which * B2_MAX_LEVELS + buf];
@@ -282,6 +283,15 @@ B2_HD bool b2_uturn(const G& g, int D, const T* var,
 template <typename T, typename G>
 B2_HD void b2_copy(const G& g, int D, T* dst, const T* src) {
     for (int i = g.lane(); i < D; i += G::NT) dst[i] = src[i];
+}
+
+// two copies with all loads in flight together (proposal position + gradient)
+template <typename T, typename G>
+B2_HD void b2_copy2(const G& g, int D, T* dst_a, const T* src_a, T* dst_b, const T* src_b) {
+    for (int i = g.lane(); i < D; i += G::NT) {
+        const T a = src_a[i], b = src_b[i];
+        dst_a[i] = a; dst_b[i] = b;
+    }
 }
 
 // first half-kick + drift, in place on edge `e`:  integration.py:90-99
@@ -533,8 +543,7 @@ B2_HD int b2_top_merge(const G& g, const B2View<T>& w, int c, B2ChainState& s) {
     const double sub_ls = w.LV(c, 0, buf);
     const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_TOP, (uint32_t)d_old, 0u);
     if (B2M<T>::log_(u) < sub_ls - s.log_size) {                   // nuts.py:289-291
-        b2_copy(g, w.D, w.V(B2_V_PROPQ, c), w.S(buf, B2_S_Q, c));
-        b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.S(buf, B2_S_G, c));
+        b2_copy2(g, w.D, w.V(B2_V_PROPQ, c), w.S(buf, B2_S_Q, c), w.V(B2_V_PROPG, c), w.S(buf, B2_S_G, c));
         s.prop_energy = w.LV(c, 2, buf);
         s.prop_logp = w.LV(c, 3, buf);
     }
@@ -598,8 +607,10 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const int b1 = b2_map_get(s.slot_map, k);
             const int b2i = b2_map_get(s.slot_map, k > 0 ? k - 1 : 0);
             const bool leaf2 = (k == 0);
+            // t2 always ends in the leaf that was just finished: its p_last is the edge's momentum (on chip), and the
+            // p_last of an intermediate result is never read -- only the chain's last merge stores it
             const T* f2 = leaf2 ? pe : w.S(b2i, B2_S_PFIRST, c);
-            const T* l2 = leaf2 ? pe : w.S(b2i, B2_S_PLAST, c);
+            const T* l2 = pe;
             const T* s2 = leaf2 ? pe : w.S(b2i, B2_S_PSUM, c);
             const T* q2 = leaf2 ? qe : w.S(b2i, B2_S_Q, c);
             const T* g2 = leaf2 ? ge : w.S(b2i, B2_S_G, c);
@@ -609,7 +620,8 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const double lp2 = leaf2 ? logp_new : w.LV(c, 3, b2i);
             T *f1 = w.S(b1, B2_S_PFIRST, c), *l1 = w.S(b1, B2_S_PLAST, c), *s1 = w.S(b1, B2_S_PSUM, c);
             // k == 0: t1 is the single leaf stored one step ago (p_first stands for its p_last and p_sum)
-            const bool turning = b2_uturn<T, G>(g, w.D, var, f1, leaf2 ? f1 : l1, leaf2 ? f1 : s1, f2, l2, s2, k > 0, s1, l1);
+            const bool turning = b2_uturn<T, G>(g, w.D, var, f1, leaf2 ? f1 : l1, leaf2 ? f1 : s1, f2, l2, s2, k > 0, s1,
+                                                k == j - 1 ? l1 : (T*)0);
             if (turning) { s.turned = 1; break; }
             const double ls1 = w.LV(c, 0, b1);
             const double la1 = w.LV(c, 1, b1);
@@ -621,8 +633,7 @@ B2_HD int b2_finish_leaf(const G& g, const B2View<T>& w, int c, B2ChainState& s,
             const double u = b2_uniform(s.key0, s.key1, (uint32_t)s.iter, B2_PURPOSE_MERGE, (uint32_t)s.depth,
                                         ((uint32_t)(k + 1) << 16) | (uint32_t)n);
             if (B2M<T>::log_(u) < ls2 - ls) {                      // nuts.py:375-378
-                b2_copy(g, w.D, w.S(b1, B2_S_Q, c), q2);
-                b2_copy(g, w.D, w.S(b1, B2_S_G, c), g2);
+                b2_copy2(g, w.D, w.S(b1, B2_S_Q, c), q2, w.S(b1, B2_S_G, c), g2);
                 w.LV(c, 2, b1) = en2; w.LV(c, 3, b1) = lp2;
             }
             w.LV(c, 0, b1) = ls;
@@ -661,8 +672,7 @@ B2_HD int b2_finish_hmc_step(const G& g, const B2View<T>& w, int c, B2ChainState
     }
     s.diverged = div ? 1 : 0;
     if (accepted) {
-        b2_copy(g, w.D, w.V(B2_V_PROPQ, c), w.V(B2_V_QE1, c));
-        b2_copy(g, w.D, w.V(B2_V_PROPG, c), w.V(B2_V_GE1, c));
+        b2_copy2(g, w.D, w.V(B2_V_PROPQ, c), w.V(B2_V_QE1, c), w.V(B2_V_PROPG, c), w.V(B2_V_GE1, c));
         s.cur_logp = logp_new;
     }
     es.accept_stat = accept; es.energy = energy; es.energy_error = de; es.model_logp = logp_new;

@@ -103,10 +103,18 @@ __global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w, int 
 // hot != null: shared memory for this chain's first w.hot_slots vector slots (B2View::hot), loaded once,
 // written back when the chain's run ends -- the persistent kernel then touches HBM/L2 only for the stack
 // buffers, the Welford windows, the trace and (hot_slots == B2_V_EVERY_LEAPFROG) the once-per-doubling slots.
+// lvh: shared memory for the chain's per-level scalars (log weights, energy, logp of the stack buffers).
 template <typename T, typename G>
-__device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const B2ModelData& m, int c, T* hot) {
+__device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const B2ModelData& m, int c, T* hot, double* lvh,
+                                                T* data_chip) {
     B2ChainState s = w.st[c];
     if (s.phase == B2_PHASE_FAILED || (s.phase == B2_PHASE_DONE && s.iter >= w.iter_cap)) return;
+    {
+        const double* src = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
+        for (int i = g.lane(); i < 4 * B2_MAX_LEVELS; i += G::NT) lvh[i] = src[i];
+        g.sync();
+        w.lv_hot = lvh;
+    }
     if (hot) {
         for (int slot = 0; slot < w.hot_slots; ++slot) {
             const T* src = w.Vglobal(slot, c);
@@ -120,12 +128,18 @@ __device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const 
         s.phase = B2_PHASE_RESUME;
         b2_advance<T, G>(g, w, c, s, 0.0);
     }
+    B2ModelData mc = m;
+    if (data_chip) {                                        // the data vector in the vector dtype, next to the hot slots
+        for (int i = g.lane(); i < m.N; i += G::NT) data_chip[i] = (T)m.aux0[i];
+        g.sync();
+        mc.aux0_chip = data_chip;
+    }
     bool active = b2_needs_grad(s.phase);
     while (active) {
         const T* q = w.V(B2_V_QE0 + s.sel, c);
         T* gr = w.V(B2_V_GE0 + s.sel, c);
         g.sync();
-        const double lp = b2_eval_model<T, G>(g, m, q, gr, c);
+        const double lp = b2_eval_model<T, G>(g, mc, q, gr, c);
         g.sync();
         active = b2_advance<T, G>(g, w, c, s, lp);
     }
@@ -137,35 +151,44 @@ __device__ __forceinline__ void persistent_body(const G& g, B2View<T>& w, const 
             for (int i = g.lane(); i < w.Dp; i += G::NT) dst[i] = src[i];
         }
     }
+    {
+        g.sync();
+        double* dst = w.lv + (size_t)c * 4 * B2_MAX_LEVELS;
+        for (int i = g.lane(); i < 4 * B2_MAX_LEVELS; i += G::NT) dst[i] = lvh[i];
+    }
     if (g.lane() == 0) w.st[c] = s;
 }
 
 template <typename T>
 __global__ void k_persistent_warp(B2View<T> w, B2ModelData m, int hot_elems) {
     extern __shared__ __align__(16) unsigned char hot_raw[];
+    __shared__ double lvh[B2_WARPS_PER_BLOCK][4 * B2_MAX_LEVELS];
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= w.C) return;
     B2WarpGroup g;
-    persistent_body<T, B2WarpGroup>(g, w, m, c, hot_elems ? reinterpret_cast<T*>(hot_raw) + (size_t)(threadIdx.x >> 5) * hot_elems : (T*)0);
+    persistent_body<T, B2WarpGroup>(g, w, m, c, hot_elems ? reinterpret_cast<T*>(hot_raw) + (size_t)(threadIdx.x >> 5) * hot_elems : (T*)0,
+                                    lvh[threadIdx.x >> 5], (T*)0);
 }
 
 // NT threads own one chain.  At D ~ 3000 all 11 hot slots take 128 KB of shared memory (fp32): one block per SM,
 // which then has to bring enough warps itself (NT = 512).  With only the 7 every-leapfrog slots on chip (82 KB) two
 // blocks share an SM (CTAS = 2): the barriers and L2 round trips of one chain's step are filled by the other chain.
 template <typename T, int NT, int CTAS>
-__global__ void __launch_bounds__(NT, CTAS) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems) {
+__global__ void __launch_bounds__(NT, CTAS) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems, int data_chip) {
     extern __shared__ __align__(16) unsigned char hot_raw[];
     __shared__ double red[8 * (NT / 32)];
+    __shared__ double lvh[4 * B2_MAX_LEVELS];
     B2BlockGroup<NT> g;
     g.red = red;
-    persistent_body<T, B2BlockGroup<NT>>(g, w, m, blockIdx.x, hot_elems ? reinterpret_cast<T*>(hot_raw) : (T*)0);
+    persistent_body<T, B2BlockGroup<NT>>(g, w, m, blockIdx.x, hot_elems ? reinterpret_cast<T*>(hot_raw) : (T*)0, lvh,
+                                         data_chip ? reinterpret_cast<T*>(hot_raw) + hot_elems : (T*)0);
 }
 
 template <typename T, int NT, int CTAS>
-static int launch_persistent_block(b2_engine* e, const B2View<T>& w, int hot_elems, size_t hot_bytes, cudaStream_t s) {
+static int launch_persistent_block(b2_engine* e, const B2View<T>& w, int hot_elems, size_t hot_bytes, int data_chip, cudaStream_t s) {
     if (hot_bytes > 48 * 1024)
         B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_block<T, NT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
-    k_persistent_block<T, NT, CTAS><<<e->C, NT, hot_bytes, s>>>(w, e->md, hot_elems);
+    k_persistent_block<T, NT, CTAS><<<e->C, NT, hot_bytes, s>>>(w, e->md, hot_elems, data_chip);
     return 0;
 }
 
@@ -300,7 +323,7 @@ extern "C" int b2_engine_create(const b2_model_desc* desc, int32_t n_chains, int
     e->C = n_chains; e->D = desc->D; e->Dp = (desc->D + 3) & ~3; e->dtype = dtype; e->device = device;
     e->md.family = desc->family; e->md.D = desc->D; e->md.N = desc->N; e->md.G = desc->G;
     e->md.aux0 = desc->d_aux0; e->md.aux1 = desc->d_aux1; e->md.X = desc->d_X; e->md.yf = desc->d_y;
-    e->md.floor_u8 = desc->d_floor; e->md.grp_off = desc->d_grp_off; e->md.scratch = nullptr;
+    e->md.floor_u8 = desc->d_floor; e->md.grp_off = desc->d_grp_off; e->md.scratch = nullptr; e->md.aux0_chip = nullptr;
     for (int i = 0; i < 4; ++i) e->md.hp[i] = desc->hp[i];
     cudaDeviceProp prop;
     B2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -476,14 +499,21 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
             w.hot_slots = B2_V_EVERY_LEAPFROG; hot_elems = w.hot_slots * e->Dp; hot_bytes = (size_t)hot_elems * sizeof(T);
         }
         if (hot_bytes > (size_t)200 * 1024) { hot_elems = 0; hot_bytes = 0; }
+        // stochastic volatility: the returns are read once per latent per leapfrog and the tree-stack traffic keeps
+        // evicting them from L1 -- a copy in the vector dtype goes next to the hot slots when it fits
+        int data_chip = 0;
+        if (blk && hot_elems && e->md.family == B2_FAMILY_STOCH_VOL && !(getenv("B2_PBLOCK_DATA") && atoi(getenv("B2_PBLOCK_DATA")) == 0)) {
+            const size_t with = hot_bytes + (size_t)e->md.N * sizeof(T);
+            if (with <= (size_t)200 * 1024 && (ctas == 1 || 2 * (with + 4096) <= smem_sm)) { data_chip = 1; hot_bytes = with; }
+        }
         if (hot_bytes > 48 * 1024 && !blk)
             B2_CUDA_OK(cudaFuncSetAttribute(k_persistent_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes));
         if (blk) {
-            int rc = ctas == 2 ? (nt == 512 ? launch_persistent_block<T, 512, 2>(e, w, hot_elems, hot_bytes, s)
-                                            : launch_persistent_block<T, 256, 2>(e, w, hot_elems, hot_bytes, s))
-                   : nt == 1024 ? launch_persistent_block<T, 1024, 1>(e, w, hot_elems, hot_bytes, s)
-                   : nt == 512  ? launch_persistent_block<T, 512, 1>(e, w, hot_elems, hot_bytes, s)
-                                : launch_persistent_block<T, 256, 1>(e, w, hot_elems, hot_bytes, s);
+            int rc = ctas == 2 ? (nt == 512 ? launch_persistent_block<T, 512, 2>(e, w, hot_elems, hot_bytes, data_chip, s)
+                                            : launch_persistent_block<T, 256, 2>(e, w, hot_elems, hot_bytes, data_chip, s))
+                   : nt == 1024 ? launch_persistent_block<T, 1024, 1>(e, w, hot_elems, hot_bytes, data_chip, s)
+                   : nt == 512  ? launch_persistent_block<T, 512, 1>(e, w, hot_elems, hot_bytes, data_chip, s)
+                                : launch_persistent_block<T, 256, 1>(e, w, hot_elems, hot_bytes, data_chip, s);
             if (rc) return rc;
         }
         else k_persistent_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, hot_bytes, s>>>(w, e->md, hot_elems);

@@ -38,6 +38,7 @@ struct B2ModelData {
     const unsigned char* floor_u8;   // [N] hier
     const int* grp_off;    // [G+1] hier: observations are sorted by group
     void* scratch;         // [C, N] T, glm group evaluator only
+    const void* aux0_chip; // optional on-chip copy of aux0 in the vector dtype (persistent block kernel, stoch. vol.)
     double hp[4];
 };
 
@@ -219,7 +220,7 @@ B2_HD double b2_eval_stoch_vol(const G& g, const B2ModelData& m, const T* q, T* 
             gv -= d * inv_s2_t;
         }
         if (i + 1 < Tn) gv += (vol[i + 1] - vi) * inv_s2_t;
-        const T r = (T)m.aux0[i];
+        const T r = m.aux0_chip ? static_cast<const T*>(m.aux0_chip)[i] : (T)m.aux0[i];
         const T z = b2_exp_t((T)-2 * vi) * (r * r * inv_nu);           // lam r^2 / nu
         const T l1 = b2_log1p_t(z);
         const T zr = z / ((T)1 + z);
