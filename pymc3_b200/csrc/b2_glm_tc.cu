@@ -873,28 +873,32 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     // halves: whole chain tiles, A gets the extra one
     const int tiles = (e->C + TC_CHAINS - 1) / TC_CHAINS;
     const int hA = ((tiles + 1) / 2) * TC_CHAINS < e->C ? ((tiles + 1) / 2) * TC_CHAINS : e->C;
-    rc = tc_ws_init(e, hs->half[0], shared, 0, hA, stream);
-    if (rc) return rc;
-    rc = tc_ws_init(e, hs->half[1], shared, hA, e->C - hA, stream);
-    if (rc) return rc;
+    if (hs->fused) {                                   // the half workspaces exist only for the fused schedule
+        rc = tc_ws_init(e, hs->half[0], shared, 0, hA, stream);
+        if (rc) return rc;
+        rc = tc_ws_init(e, hs->half[1], shared, hA, e->C - hA, stream);
+        if (rc) return rc;
+        hs->half[0].post_levels = hs->half[1].post_levels = hs->post_levels;
+    }
     hs->full.post_levels = TC_POST_STAGE_MAX;
-    hs->half[0].post_levels = hs->half[1].post_levels = hs->post_levels;
     k_glm_tc_prep_x<<<shared.n_tiles, 256, 0, stream>>>(e->md.X, e->md.yf, N, e->md.G, shared.xt, shared.n_tiles);
     B2_CUDA_OK(cudaGetLastError());
     e->launches += 1;
     const size_t fs = tc_fused_smem(hs, e->Dp);
-    if ((rc = tc_main_attr<6, 0, false>(TC_MAIN_SMEM(6)))) return rc;
-    if ((rc = tc_main_attr<6, 1, false>(TC_MAIN_SMEM(6)))) return rc;
-    if ((rc = tc_main_attr<3, 0, false>(TC_MAIN_SMEM(3)))) return rc;
-    if ((rc = tc_main_attr<3, 1, false>(TC_MAIN_SMEM(3)))) return rc;
-    if ((rc = tc_main_attr<4, 0, false>(TC_MAIN_SMEM(4)))) return rc;
-    if ((rc = tc_main_attr<4, 1, false>(TC_MAIN_SMEM(4)))) return rc;
-    if ((rc = tc_main_attr<5, 0, false>(TC_MAIN_SMEM(6)))) return rc;
-    if ((rc = tc_main_attr<5, 1, false>(TC_MAIN_SMEM(6)))) return rc;
-    if ((rc = tc_main_attr<5, 0, true>(fs))) return rc;
-    if ((rc = tc_main_attr<5, 1, true>(fs))) return rc;
-    if ((rc = tc_main_attr<4, 0, true>(fs))) return rc;
-    if ((rc = tc_main_attr<4, 1, true>(fs))) return rc;
+    // only the instantiation this engine launches (each first touch of a kernel loads its code: module loading is lazy)
+    const int su_ = hs->stages_unfused, ep_ = hs->epi;
+#define TC_ATTR(S, E, F, BYTES) do { if ((rc = tc_main_attr<S, E, F>(BYTES))) return rc; } while (0)
+    if (!hs->fused || env_int("B2_TC_HOOK_FUSED", 0) == 0) {
+        if (su_ == 3) { if (ep_) TC_ATTR(3, 1, false, TC_MAIN_SMEM(3)); else TC_ATTR(3, 0, false, TC_MAIN_SMEM(3)); }
+        else if (su_ == 4) { if (ep_) TC_ATTR(4, 1, false, TC_MAIN_SMEM(4)); else TC_ATTR(4, 0, false, TC_MAIN_SMEM(4)); }
+        else if (su_ == 5) { if (ep_) TC_ATTR(5, 1, false, TC_MAIN_SMEM(6)); else TC_ATTR(5, 0, false, TC_MAIN_SMEM(6)); }
+        else { if (ep_) TC_ATTR(6, 1, false, TC_MAIN_SMEM(6)); else TC_ATTR(6, 0, false, TC_MAIN_SMEM(6)); }
+    }
+    if (hs->fused || env_int("B2_TC_HOOK_FUSED", 0)) {
+        if (hs->stages_fused == 5) { if (ep_) TC_ATTR(5, 1, true, fs); else TC_ATTR(5, 0, true, fs); }
+        else { if (ep_) TC_ATTR(4, 1, true, fs); else TC_ATTR(4, 0, true, fs); }
+    }
+#undef TC_ATTR
     B2_CUDA_OK(cudaFuncSetAttribute(k_glm_tc_post, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(4 * tc_post_warp_smem(e->Dp, TC_POST_STAGE_MAX))));
     e->glm_tc = hs;            // owned by the engine; released in b2_glm_tc_release

@@ -161,17 +161,18 @@ def _check_start_shape(model, start):
 
 
 def _start_array(model, start, chains):
+    """[chains, ndim] start positions; variables a start dict lacks come from the test point (update_start_vals,
+    sampling.py:1900-1926).  One pass per variable over all chains, not a dict_to_array per chain."""
     out = np.empty((chains, model.ndim))
     test_point = model.test_point
-    last, last_row = None, None
-    for c in range(chains):
-        if start[c] is last:                      # the same dict for every chain (start=None, a single start point)
-            out[c] = last_row
-            continue
+    if all(start[c] is start[0] for c in range(chains)):          # start=None or a single start point
         point = dict(test_point)
-        point.update({k: v for k, v in start[c].items() if k in point})       # update_start_vals
-        out[c] = model.dict_to_array(point)
-        last, last_row = start[c], out[c]
+        point.update({k: v for k, v in start[0].items() if k in point})
+        out[:] = model.dict_to_array(point)
+        return out
+    for vm in model.ordering().vmap:
+        default = np.ravel(test_point[vm.var])
+        out[:, vm.slc] = np.stack([np.ravel(s[vm.var]) if vm.var in s else default for s in start[:chains]])
     return out
 
 
@@ -215,11 +216,15 @@ class _ShardRun:
         import queue
         import torch
         self.torch, self.step, self.draws = torch, step, draws
+        t0 = time.perf_counter()
         self.eng = step._make_engine(len(q0), device=dev)
+        t1 = time.perf_counter()
         step._init_engine_state(self.eng, q0, seeds)
+        t2 = time.perf_counter()
         self.trace = self.eng.alloc_trace(step._kind, draws)
         self.host = {k: np.empty(tuple(v.shape), dtype=_np_dtype(v)) for k, v in self.trace.items()}
         self.copy_stream = torch.cuda.Stream(device=self.eng.dev)
+        self.init_phases = {"engine": t1 - t0, "state": t2 - t1, "trace_buffers": time.perf_counter() - t2}
         self.rows_done = 0
         self.device_seconds = 0.0
         self.chunk_log = []                   # (rows done, wall clock, device seconds, leapfrogs so far) after every chunk
@@ -309,8 +314,9 @@ class _ShardRun:
         out = (self.eng.reports(), self.eng.mass_var(), self.eng.kernel_launches())
         t2 = time.perf_counter()
         self.eng.close()
+        t3 = time.perf_counter()
         self.trace = None
-        self.finish_phases = {"copies": t1 - t0, "reports": t2 - t1, "release": time.perf_counter() - t2}
+        self.finish_phases = {"copies": t1 - t0, "reports": t2 - t1, "engine_close": t3 - t2, "trace_free": time.perf_counter() - t3}
         return out
 
 
@@ -407,7 +413,7 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     step._last_device_seconds = max(r.device_seconds for r in runs)
     step._last_chunk_log = [(rows_, t_ - tm["t0"], d_, g_) for rows_, t_, d_, g_ in runs[0].chunk_log]
     step._last_n_grad = int(sum(rep.n_grad for rep in reports))
-    step._last_finish_phases = runs[0].finish_phases
+    step._last_finish_phases = dict(runs[0].finish_phases, **{"init_" + k: v for k, v in runs[0].init_phases.items()})
 
     for c, rep in enumerate(reports):
         if rep.phase == _capi.PHASE_FAILED:
