@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 3
+#define B2_ABI_VERSION 4
 
 enum b2_dtype { B2_F32 = 0, B2_F64 = 1 };
 
@@ -141,6 +141,16 @@ int b2_logp_dlogp(b2_engine* e, const void* d_q, int32_t n_points, double* d_log
  * edge slots and mass diagonal as scratch: call b2_set_state again before sampling. */
 int b2_leapfrog(b2_engine* e, const void* d_q, const void* d_p, const double* d_var, double epsilon,
                 int32_t n_steps, void* d_q_out, void* d_p_out, double* d_energy_out, int32_t glm_path, void* stream);
+
+/* replaces QuadPotentialFull / QuadPotentialFullInv (quadpotential.py:400-479: velocity = cov p, energy = p.cov p / 2,
+ * random = chol^-T n) for every chain of the engine.  d_chol [D, D] row-major (engine dtype) is the LOWER Cholesky
+ * factor L of the covariance (cov = L L^T); it is copied, the pointer is not retained.  From then on the state
+ * machine integrates z = L^-1 q with unit mass -- the same Hamiltonian flow, U-turn products and energies as the
+ * dense metric on q (p_z = L^T p_q) -- and evaluates the density at q = L z, mapping its gradient back with L^T:
+ * positions handed to b2_set_state / b2_set_position and returned in traces / b2_get_position are z (the host side
+ * multiplies by L).  Runs become lock-step, mass adaptation must be off (adapt_mass = 0), mass var = 1.
+ * d_chol = NULL switches the dense metric off.  Not available in the stepwise (b2_step_*) run. */
+int b2_set_dense_mass(b2_engine* e, const void* d_chol, void* stream);
 
 /* replaces per-chain seeding + start points + init_nuts' potential
  * (sampling.py:410-413, 883-884, 1915-1929; base_hmc.py:93-103):

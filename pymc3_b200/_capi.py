@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200nuts.so")
 
-ABI_VERSION = 3          # include/b200nuts.h B2_ABI_VERSION this binding's struct layouts were written for
+ABI_VERSION = 4          # include/b200nuts.h B2_ABI_VERSION this binding's struct layouts were written for
 B2_F32, B2_F64 = 0, 1
 B2_STD_NORMAL, B2_EIGHT_SCHOOLS_NCP, B2_GLM_LOGIT, B2_HIER_LINEAR_NCP, B2_STOCH_VOL = 0, 2, 3, 4, 5
 B2_NUTS, B2_HMC = 0, 1
@@ -54,7 +54,7 @@ class ChainReport(C.Structure):
 EXPORTS = ["b2_abi_version", "b2_last_error", "b2_engine_create", "b2_engine_destroy", "b2_logp_dlogp",
            "b2_set_state", "b2_set_position", "b2_sample_run", "b2_get_chain_reports", "b2_get_mass_var", "b2_get_position",
            "b2_kernel_launches", "b2_set_profiling", "b2_get_profile", "b2_get_profile_advance", "b2_step_begin", "b2_step_likelihood",
-           "b2_step_advance", "b2_step_active", "b2_step_end", "b2_leapfrog"]
+           "b2_step_advance", "b2_step_active", "b2_step_end", "b2_leapfrog", "b2_set_dense_mass"]
 
 _lib = None
 
@@ -92,6 +92,7 @@ def load_library(path=None):
     lib.b2_step_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.b2_step_active.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
     lib.b2_step_end.argtypes = [C.c_void_p]
+    lib.b2_set_dense_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b2_leapfrog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.b2_get_profile_advance.argtypes = [C.c_void_p, C.POINTER(C.c_double)]

@@ -351,6 +351,7 @@ extern "C" int b2_engine_destroy(b2_engine* e) {
     b2_glm_tc_release(e);
     b2_glm_tcw_release(e);
     cudaFree(e->glm_scratch); cudaFree(e->d_active); cudaFree(e->glm_ws); cudaFree(e->hier_ws);
+    cudaFree(e->dense_L); cudaFree(e->dense_Lt); cudaFree(e->dense_q); cudaFree(e->dense_g);
     cudaFreeHost(e->h_active);
     if (e->own_stream) { cudaStreamDestroy(e->own_stream); cudaEventDestroy(e->own_event); }
     if (e->ev[0]) for (int i = 0; i < 96; ++i) cudaEventDestroy(e->ev[i]);
@@ -421,6 +422,82 @@ extern "C" int b2_set_position(b2_engine* e, const void* d_q, void* stream) {
     return 0;
 }
 
+// ------------------------------------------------------------------ dense mass matrix (reparameterised run)
+// One warp per chain.  fwd: q = L z for the chain's pending position (the edge st[c].sel points at);
+// bwd: grad_z = L^T grad_q written to that edge's gradient slot.  Lt / L are read with consecutive lanes on
+// consecutive addresses; the chain's vector is staged in shared memory.  D x D multiply-adds per chain and pass:
+// noise next to a likelihood over N observations.
+template <typename T>
+__global__ void k_dense_fwd(const T* __restrict__ Lt, int D, int Dp, const T* zA, const T* zB, const B2ChainState* st, int C, T* q_out) {
+    extern __shared__ __align__(16) unsigned char dense_raw[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (c >= C || !b2_needs_grad(st[c].phase)) return;
+    T* z = reinterpret_cast<T*>(dense_raw) + (size_t)wib * Dp;
+    const T* src = (st[c].sel ? zB : zA) + (size_t)c * Dp;
+    for (int i = lane; i < D; i += 32) z[i] = src[i];
+    __syncwarp();
+    for (int i = lane; i < D; i += 32) {
+        T acc = (T)0;
+        for (int j = 0; j <= i; ++j) acc += Lt[(size_t)j * D + i] * z[j];      // L[i][j], j <= i
+        q_out[(size_t)c * Dp + i] = acc;
+    }
+}
+
+template <typename T>
+__global__ void k_dense_bwd(const T* __restrict__ L, int D, int Dp, const T* g_in, T* gA, T* gB, const B2ChainState* st, int C) {
+    extern __shared__ __align__(16) unsigned char dense_raw[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (c >= C || !b2_needs_grad(st[c].phase)) return;
+    T* g = reinterpret_cast<T*>(dense_raw) + (size_t)wib * Dp;
+    for (int i = lane; i < D; i += 32) g[i] = g_in[(size_t)c * Dp + i];
+    __syncwarp();
+    T* dst = (st[c].sel ? gB : gA) + (size_t)c * Dp;
+    for (int j = lane; j < D; j += 32) {
+        T acc = (T)0;
+        for (int i = j; i < D; ++i) acc += L[(size_t)i * D + j] * g[i];        // (L^T g)_j = sum_{i >= j} L[i][j] g[i]
+        dst[j] = acc;
+    }
+}
+
+template <typename T>
+__global__ void k_dense_prepare(const T* chol, int D, T* L, T* Lt) {       // keeps the lower triangle only
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D * D) return;
+    const int i = idx / D, j = idx % D;
+    const T v = j <= i ? chol[idx] : (T)0;
+    L[idx] = v;
+    Lt[(size_t)j * D + i] = v;
+}
+
+extern "C" int b2_set_dense_mass(b2_engine* e, const void* d_chol, void* stream) {
+    if (!e) { b2_set_error("b2_set_dense_mass: null engine"); return -1; }
+    if (e->stepping) { b2_set_error("b2_set_dense_mass: a stepwise run is in progress"); return -6; }
+    B2_CUDA_OK(cudaSetDevice(e->device));
+    if (!d_chol) {
+        cudaFree(e->dense_L); cudaFree(e->dense_Lt); cudaFree(e->dense_q); cudaFree(e->dense_g);
+        e->dense_L = e->dense_Lt = e->dense_q = e->dense_g = nullptr;
+        return 0;
+    }
+    if (e->D > 1024) { b2_set_error("b2_set_dense_mass: D > 1024 (a D x D factor per leapfrog and chain) is not supported"); return -5; }
+    const size_t el = e->dtype == B2_F64 ? 8 : 4;
+    if (!e->dense_L) {
+        B2_CUDA_OK(cudaMalloc(&e->dense_L, (size_t)e->D * e->D * el));
+        B2_CUDA_OK(cudaMalloc(&e->dense_Lt, (size_t)e->D * e->D * el));
+        B2_CUDA_OK(cudaMalloc(&e->dense_q, (size_t)e->C * e->Dp * el));
+        B2_CUDA_OK(cudaMalloc(&e->dense_g, (size_t)e->C * e->Dp * el));
+        B2_CUDA_OK(cudaMemsetAsync(e->dense_q, 0, (size_t)e->C * e->Dp * el, (cudaStream_t)stream));
+        B2_CUDA_OK(cudaMemsetAsync(e->dense_g, 0, (size_t)e->C * e->Dp * el, (cudaStream_t)stream));
+    }
+    const int n = e->D * e->D;
+    if (e->dtype == B2_F64) k_dense_prepare<double><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const double*)d_chol, e->D, (double*)e->dense_L, (double*)e->dense_Lt);
+    else k_dense_prepare<float><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)d_chol, e->D, (float*)e->dense_L, (float*)e->dense_Lt);
+    e->launches += 1;
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static bool persistent_ok(const b2_engine* e) {
     switch (e->md.family) {
     case B2_FAMILY_STD_NORMAL:
@@ -473,6 +550,11 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
     B2View<T> w = build_view<T>(e, o, tr);
     int mode = o->exec_mode;
     if (mode == B2_EXEC_AUTO) mode = persistent_ok(e) ? B2_EXEC_PERSISTENT : B2_EXEC_LOCKSTEP;
+    const bool dense = e->dense_L != nullptr;
+    if (dense) {
+        if (o->adapt_mass) { b2_set_error("b2_sample_run: a dense mass matrix is static (adapt_mass must be 0)"); return -5; }
+        mode = B2_EXEC_LOCKSTEP;                      // the reparameterisation wraps the chain-batched likelihood launch
+    }
     if (mode == B2_EXEC_PERSISTENT && e->md.family == B2_FAMILY_GLM_LOGIT) {
         int rc = ensure_glm_scratch(e);
         if (rc) return rc;
@@ -527,7 +609,7 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         // fast chains may run ahead of this call's last iteration (rows exist in the caller's trace buffers)
         if (o->run_ahead > 0) w.iter_cap = w.iter_end + o->run_ahead;
         // GLM on the tensor-core path: {tcgen05 likelihood, fused finalize+advance+repack} per step
-        const bool fused_tc = sizeof(T) == 4 && !blk && e->md.family == B2_FAMILY_GLM_LOGIT &&
+        const bool fused_tc = sizeof(T) == 4 && !blk && !dense && e->md.family == B2_FAMILY_GLM_LOGIT &&
                               pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05 && !b2_glm_tcw_supported(e);
         if (fused_tc && !b2_glm_tc_supported(e)) { b2_set_error("tcgen05 GLM path does not support this shape"); return -6; }
         if (e->iter_done > 0) {                       // re-activate chains that finished the previous call
@@ -539,7 +621,14 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
             int rc = b2_glm_tc_pack(e, (const float*)qA, (const float*)qB, e->Dp, e->st, e->C, s);
             if (rc) return rc;
         } else if (sizeof(T) == 4 && b2_glm_tcw_supported(e) && pick_glm_path(e, o->glm_path) == B2_GLM_TCGEN05) {
-            int rc = b2_glm_tcw_refresh(e, (const float*)qA, (const float*)qB, e->Dp, e->st, e->C, s);   // reference position of this run
+            const float *rA = (const float*)qA, *rB = (const float*)qB;
+            if (dense) {                                  // the likelihood sees q = L z: centre the reference there
+                k_dense_fwd<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, (size_t)B2_WARPS_PER_BLOCK * e->Dp * sizeof(T), s>>>(
+                    (const T*)e->dense_Lt, e->D, e->Dp, qA, qB, e->st, e->C, (T*)e->dense_q);
+                e->launches += 1;
+                rA = rB = (const float*)e->dense_q;
+            }
+            int rc = b2_glm_tcw_refresh(e, rA, rB, e->Dp, e->st, e->C, s);   // reference position of this run
             if (rc) return rc;
         }
         // one batch = `batch` leapfrogs of every live chain + the count of chains that still owe transitions
@@ -551,8 +640,19 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
                     int rc = b2_glm_tc_step(e, &w, s, e->profile ? e->ev[3 * b + 1] : (cudaEvent_t)0);
                     if (rc) return rc;
                 } else {
-                    int rc = launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
-                    if (rc) return rc;
+                    int rc;
+                    if (dense) {                          // q = L z  ->  logp, grad_q  ->  grad_z = L^T grad_q
+                        T *dq = (T*)e->dense_q, *dg = (T*)e->dense_g;
+                        const size_t sm = (size_t)B2_WARPS_PER_BLOCK * e->Dp * sizeof(T);
+                        k_dense_fwd<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, sm, s>>>((const T*)e->dense_Lt, e->D, e->Dp, qA, qB, e->st, e->C, dq);
+                        rc = launch_likelihood<T>(e, dq, dq, dg, dg, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
+                        if (rc) return rc;
+                        k_dense_bwd<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, sm, s>>>((const T*)e->dense_L, e->D, e->Dp, dg, gA, gB, e->st, e->C);
+                        e->launches += 2;
+                    } else {
+                        rc = launch_likelihood<T>(e, qA, qB, gA, gB, e->Dp, e->st, e->C, e->logp_eval, o->glm_path, s);
+                        if (rc) return rc;
+                    }
                     if (e->profile) cudaEventRecord(e->ev[3 * b + 1], s);
                     if (blk) k_advance_block<T><<<e->C, B2_BLOCK_NT, 0, s>>>(w, 0);
                     else k_advance_warp<T><<<nb_warp, 32 * B2_WARPS_PER_BLOCK, 0, s>>>(w, 0);
@@ -804,6 +904,7 @@ static int step_advance_t(b2_engine* e, const double* d_packed, int prior_copies
 extern "C" int b2_step_begin(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* trace, void* stream) {
     const int rc0 = check_run_args("b2_step_begin", e, o);
     if (rc0) return rc0;
+    if (e->dense_L) { b2_set_error("b2_step_begin: the stepwise run does not support a dense mass matrix"); return -5; }
     B2_CUDA_OK(cudaSetDevice(e->device));
     e->step_opts = *o;
     memset(&e->step_trace, 0, sizeof(e->step_trace));

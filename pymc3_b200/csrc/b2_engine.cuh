@@ -39,6 +39,9 @@ struct b2_engine {
     int64_t like_n;
     double adv_ms;             // advance / post kernel, same launches
     cudaEvent_t ev[96];        // per batch step b: ev[3b] | likelihood | ev[3b+1] | advance | ev[3b+2]
+    // dense mass matrix (b2_set_dense_mass): the state machine runs in z = L^-1 q with unit mass; L is the lower
+    // Cholesky factor of the covariance.  dense_L [D][D] row-major, dense_Lt its transpose, dense_q / dense_g [C][Dp].
+    void *dense_L, *dense_Lt, *dense_q, *dense_g;
     cudaStream_t own_stream;   // b2_sample_run's stream when the caller hands over the (uncapturable) default stream
     cudaEvent_t own_event;
 };

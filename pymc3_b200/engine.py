@@ -49,6 +49,7 @@ class Engine:
                                               self.device, C.byref(handle)), self.lib)
         self.handle = handle
         self.iter_done = 0
+        self._chol = self._chol_t = None
 
     # -- plumbing
     def _upload(self, array, dtype):
@@ -110,9 +111,34 @@ class Engine:
                                          int(glm_path), self._stream()), self.lib)
         return q_out, p_out, energy
 
+    # -- QuadPotentialFull / FullInv (quadpotential.py:400-479) for every chain: the device integrates z = L^-1 q
+    def set_dense_mass(self, chol):
+        """chol: [D, D] lower Cholesky factor of the covariance (None switches the dense metric off).  The engine
+        then samples z = L^-1 q with unit mass (b2_set_dense_mass); this class converts at its boundary, so callers
+        keep handing over and receiving q: set_state / set_position take q, run() and position() return q."""
+        torch = self.torch
+        if chol is None:
+            _capi.check(self.lib.b2_set_dense_mass(self.handle, None, self._stream()), self.lib)
+            self._chol = self._chol_t = None
+            return
+        L = np.tril(np.asarray(chol, dtype="f8"))
+        if L.shape != (self.D, self.D):
+            raise ValueError("chol must have shape (%d, %d)" % (self.D, self.D))
+        self._chol = L
+        self._chol_t = torch.as_tensor(np.ascontiguousarray(L.T), device=self.dev).to(self.t_dtype)     # q = z @ L^T
+        t = torch.as_tensor(np.ascontiguousarray(L), device=self.dev).to(self.t_dtype).contiguous()
+        _capi.check(self.lib.b2_set_dense_mass(self.handle, t.data_ptr(), self._stream()), self.lib)
+        torch.cuda.synchronize(self.dev)               # `t` is copied by the call; it may go now
+
+    def _to_z(self, q):
+        import scipy.linalg
+        return scipy.linalg.solve_triangular(self._chol, np.asarray(q, dtype="f8").T, lower=True).T
+
     # -- sampling.py:410-413, 883-884, 1915-1929 + base_hmc.py:93-103
     def set_state(self, q0, seeds, step_size0, mass_mean, mass_var, mass_weight, adaptation_window=101):
         torch = self.torch
+        if self._chol is not None:
+            q0 = self._to_z(np.asarray(q0, dtype="f8").reshape(self.n_chains, self.D))
         q0 = np.asarray(q0, dtype=self.np_dtype).reshape(self.n_chains, self.D)
         self._q0 = torch.as_tensor(np.ascontiguousarray(q0), device=self.dev)
         self._seeds = torch.as_tensor(np.asarray(seeds, dtype=np.uint64).view(np.int64).copy(), device=self.dev)
@@ -126,6 +152,8 @@ class Engine:
         self.iter_done = 0
 
     def set_position(self, q):
+        if self._chol is not None:
+            q = self._to_z(np.asarray(q, dtype="f8").reshape(self.n_chains, self.D))
         q = np.asarray(q, dtype=self.np_dtype).reshape(self.n_chains, self.D)
         t = self.torch.as_tensor(np.ascontiguousarray(q), device=self.dev)
         _capi.check(self.lib.b2_set_position(self.handle, t.data_ptr(), self._stream()), self.lib)
@@ -166,6 +194,8 @@ class Engine:
             o.run_ahead = int(next(iter(out.values())).shape[0] - row0 - n_iters)
         _capi.check(self.lib.b2_sample_run(self.handle, C.byref(o), C.byref(tr), self._stream()), self.lib)
         self.iter_done += int(n_iters)
+        if self._chol is not None and "q" in view:      # rows of this call are complete: z -> q = L z, in place
+            view["q"].copy_(view["q"] @ self._chol_t)
         return view
 
     def reports(self):
@@ -181,7 +211,7 @@ class Engine:
     def position(self):
         out = np.empty((self.n_chains, self.D))
         _capi.check(self.lib.b2_get_position(self.handle, out.ctypes.data), self.lib)
-        return out
+        return out @ self._chol.T if self._chol is not None else out
 
     def set_profiling(self, on=True):
         _capi.check(self.lib.b2_set_profiling(self.handle, int(bool(on))), self.lib)

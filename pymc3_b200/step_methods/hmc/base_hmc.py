@@ -16,7 +16,8 @@ from ...backends.report import SamplerWarning, WarningType
 from ...exceptions import SamplingError
 from ...model import modelcontext
 from .. import step_sizes
-from .quadpotential import QuadPotentialDiag, QuadPotentialDiagAdapt, quad_potential
+from .quadpotential import (QuadPotentialDiag, QuadPotentialDiagAdapt, QuadPotentialFull, QuadPotentialFullInv,
+                            quad_potential)
 
 logger = logging.getLogger("pymc3")
 
@@ -81,7 +82,9 @@ class BaseHMC:
         # QuadPotential protocol (a user subclass overriding velocity / energy / random / update, test_quadpotential.py:
         # 138-155; a custom step_rand callable) is honoured by driving the tree from the host and calling the user's
         # object per leapfrog, with logp / dlogp still evaluated on the device (host_transition.py).
-        self._host_driven = type(self.potential) not in (QuadPotentialDiag, QuadPotentialDiagAdapt)
+        # Exactly QuadPotentialFull / FullInv (static dense) also run on the device, in z = L^-1 q (engine.set_dense_mass).
+        self._dense = type(self.potential) in (QuadPotentialFull, QuadPotentialFullInv) and size <= 1024
+        self._host_driven = type(self.potential) not in (QuadPotentialDiag, QuadPotentialDiagAdapt) and not self._dense
         if self._host_driven and not all(hasattr(self.potential, m) for m in ("velocity", "energy", "random")):
             raise TypeError("potential must implement the QuadPotential protocol (velocity, energy, random); "
                             "got %r" % type(self.potential).__name__)
@@ -133,6 +136,8 @@ class BaseHMC:
 
     def _init_engine_state(self, engine, q0, seeds):
         init = self.potential.device_init()
+        if self._dense:
+            engine.set_dense_mass(self.potential.device_chol())
         engine.set_state(q0, seeds, self._initial_step, init["mean"], init["var"], init["weight"], init["window"])
 
     # -- one chain, one draw (arraystep.py:258-264 + base_hmc.py:133-199)

@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert set(names) == set(_capi.EXPORTS)
-    assert _capi.load_library().b2_abi_version() == _capi.ABI_VERSION == 3
+    assert _capi.load_library().b2_abi_version() == _capi.ABI_VERSION == 4
 
 
 def test_ctypes_structs_match_header_layout():
@@ -250,9 +250,11 @@ def test_host_driven_transitions_sample_the_target():
     assert np.allclose(np.std(draws, axis=0), sig, rtol=0.1)
 
 
-def test_sample_with_a_dense_potential_runs_host_driven_chains():
-    """sample() with a step method that is driven from the host (dense scaling -> QuadPotentialFull): sequential
-    chains, per-draw record, sampler stats; the density here is a NumPy stand-in for the device ValueGradFunction."""
+def test_sample_with_an_adaptive_dense_potential_runs_host_driven_chains():
+    """sample() with a step method that is driven from the host (QuadPotentialFullAdapt, quadpotential.py:482-572;
+    tests/test_quadpotential.py:274-290): sequential chains, per-draw record, sampler stats; the density here is a
+    NumPy stand-in for the device ValueGradFunction."""
+    from pymc3_b200.step_methods.hmc.quadpotential import QuadPotentialFullAdapt
     sig = np.array([1.0, 2.0, 0.5])
 
     class FakeVG:
@@ -267,11 +269,67 @@ def test_sample_with_a_dense_potential_runs_host_driven_chains():
 
     seen = []
     with Model(3, sigma=sig):
-        step = pm.NUTS(scaling=np.diag(sig ** 2) + 0.05, is_cov=True, dtype="float64")
-        assert type(step.potential).__name__ == "QuadPotentialFull" and not step._batched
+        with pytest.warns(UserWarning):
+            pot = QuadPotentialFullAdapt(3, np.zeros(3), np.diag(sig ** 2) + 0.05, 5)
+        step = pm.NUTS(potential=pot, dtype="float64")
+        assert not step._batched
+        dense = pm.NUTS(scaling=np.diag(sig ** 2) + 0.05, is_cov=True, dtype="float64")
+        assert type(dense.potential).__name__ == "QuadPotentialFull" and dense._batched      # static dense: device path
         trace = pm.sample(400, tune=200, chains=2, step=step, random_seed=11, compute_convergence_checks=False,
                           callback=lambda trace, draw: seen.append(draw.draw_idx))
     x = trace["x"]
     assert x.shape == (800, 3) and np.allclose(x.std(axis=0), sig, rtol=0.2) and np.abs(x.mean(axis=0)).max() < 0.4
     assert len(seen) == 2 * 600 and 0.6 < trace.get_sampler_stats("mean_tree_accept").mean() < 0.99
     assert np.isfinite(trace.get_sampler_stats("step_size")).all()
+
+
+def test_running_covariance_and_adaptive_dense_potential():
+    """tests/test_quadpotential.py:158-271 restated for the host classes: the Welford co-moment accumulator equals
+    numpy's estimates (also when seeded with pseudo-observations), momenta drawn from the potential have covariance
+    M, the update window / adaptation window bookkeeping, the not-invertible error and the experimental warning."""
+    from pymc3_b200.step_methods.hmc import quadpotential as qp
+    rng = np.random.default_rng(5432)
+    L = np.tril(rng.normal(size=(10, 10)))
+    L[np.diag_indices(10)] = np.exp(np.diag(L))
+    samples = rng.multivariate_normal(rng.normal(size=10), L @ L.T, size=100)
+    est = qp._WeightedCovariance(10)
+    for x in samples:
+        est.add_sample(x, 1)
+    assert np.allclose(est.current_mean(), samples.mean(axis=0)) and np.allclose(est.current_covariance(), np.cov(samples, rowvar=0))
+    est2 = qp._WeightedCovariance(10, samples[:10].mean(axis=0), np.cov(samples[:10], rowvar=0, bias=True), 10)
+    for x in samples[10:]:
+        est2.add_sample(x, 1)
+    assert np.allclose(est2.current_mean(), samples.mean(axis=0)) and np.allclose(est2.current_covariance(), np.cov(samples, rowvar=0))
+
+    np.random.seed(4566)
+    m = np.array([[3.0, -2.0], [-2.0, 4.0]])
+    var = np.array([[2 * m[0, 0], m[1, 0] ** 2 + m[1, 1] * m[0, 0]], [m[0, 1] ** 2 + m[1, 1] * m[0, 0], 2 * m[1, 1]]])
+    with pytest.warns(UserWarning):
+        pot = qp.QuadPotentialFullAdapt(2, np.zeros(2), np.linalg.inv(m), 1)
+    draws = np.array([pot.random() for _ in range(1000)])
+    assert np.all(np.abs(m - np.cov(draws, rowvar=0)) < 5 * np.sqrt(var / 1000))       # Wishart spread
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        init = np.array([[1.0, 0.02], [0.02, 0.8]])
+        pot = qp.QuadPotentialFullAdapt(2, np.zeros(2), init, 1, update_window=50)
+        for _ in range(49):
+            pot.update(np.random.randn(2), None, True)
+        assert np.allclose(pot._cov, init)
+        pot.update(np.random.randn(2), None, True)
+        assert not np.allclose(pot._cov, init)
+        pot = qp.QuadPotentialFullAdapt(2, np.zeros(2), np.eye(2), 1, adaptation_window=10)
+        for _ in range(11):
+            pot.update(np.random.randn(2), None, True)
+        assert pot._previous_update == 10 and pot.adaptation_window == 10 * pot.adaptation_window_multiplier
+        pot = qp.QuadPotentialFullAdapt(2, np.zeros(2), np.eye(2), 0, adaptation_window=10)
+        for _ in range(11):
+            pot.update(np.ones(2), None, True)
+        with pytest.raises(ValueError):
+            pot.raise_ok(None)
+        # gradient-based diagonal adaptation (quadpotential.py:272-310): after 150 draws var = (n / sum |grad|)^2
+        g = qp.QuadPotentialDiagAdaptGrad(2, np.zeros(2), np.ones(2), 10)
+        for _ in range(300):
+            g.update(np.random.randn(2), np.array([2.0, -0.5]), True)
+        assert np.allclose(g._var, [0.25, 4.0], rtol=0.05)       # (the windows restart from one pseudo-gradient of 1)

@@ -298,17 +298,101 @@ def test_user_potential_is_called():
     assert set(trace.stat_names) >= {"depth", "tree_size", "mean_tree_accept", "energy", "diverging", "step_size"}
 
 
-def test_dense_mass_matrix_through_host_driven_transitions():
-    """test_step.py:534-565 in spirit: NUTS with a dense `scaling=C` (QuadPotentialFull, quadpotential.py:438-472)
-    reproduces the moments of the target."""
+def test_dense_mass_matrix_on_the_device():
+    """test_step.py:534-565 in spirit: NUTS with a dense `scaling=C` (QuadPotentialFull / FullInv, quadpotential.py:
+    400-479) runs all chains on the device in z = L^-1 q (b2_set_dense_mass) and reproduces the moments of the target;
+    the adaptive dense potential (FullAdapt) takes the host-driven path with device gradients."""
     sig = np.array([1.0, 2.0, 0.5])
+    C = np.diag(sig ** 2) + 0.05
+    for kw in (dict(scaling=C, is_cov=True), dict(scaling=np.linalg.inv(C), is_cov=False)):
+        with pm.StdNormal(3, sigma=sig):
+            step = pm.NUTS(dtype="float64", **kw)
+            assert type(step.potential).__name__ in ("QuadPotentialFull", "QuadPotentialFullInv") and step._batched
+            trace = pm.sample(500, tune=300, chains=64, step=step, random_seed=11, compute_convergence_checks=False)
+        x = trace["x"]
+        assert x.shape == (64 * 500, 3)
+        assert np.abs(x.mean(axis=0) / sig).max() < 0.05 and np.allclose(x.std(axis=0), sig, rtol=0.03)
+        assert 0.7 < trace.get_sampler_stats("mean_tree_accept").mean() < 0.95
+    from pymc3_b200.step_methods.hmc.quadpotential import QuadPotentialFullAdapt
     with pm.StdNormal(3, sigma=sig):
-        C = np.diag(sig ** 2) + 0.05
-        step = pm.NUTS(scaling=C, is_cov=True, dtype="float64")
-        assert type(step.potential).__name__ == "QuadPotentialFull" and not step._batched
-        trace = pm.sample(600, tune=300, chains=2, step=step, random_seed=11, compute_convergence_checks=False)
+        with pytest.warns(UserWarning):
+            pot = QuadPotentialFullAdapt(3, np.zeros(3), np.eye(3), 1)
+        step = pm.NUTS(potential=pot, dtype="float64")
+        assert not step._batched
+        trace = pm.sample(300, tune=300, chains=2, step=step, random_seed=11, compute_convergence_checks=False)
     x = trace["x"]
-    assert np.abs(x.mean(axis=0)).max() < 0.25 and np.allclose(x.std(axis=0), sig, rtol=0.15)
+    assert np.abs(x.mean(axis=0)).max() < 0.4 and np.allclose(x.std(axis=0), sig, rtol=0.2)
+    assert np.allclose(np.sqrt(np.diag(pot._cov)), sig, rtol=0.3)            # the potential learnt the scales
+
+
+def test_dense_metric_with_a_diagonal_factor_equals_the_diagonal_potential():
+    """The reparameterised run must be the same Markov chain as the metric it stands for: with L = diag(s) the dense
+    path (z = q / s, unit mass) and the diagonal potential var = s^2 see the same momenta (p_z = n, p_q = n / s), so
+    the fp64 traces agree to rounding until chaos takes over, and all tree statistics agree on the first draws."""
+    from pymc3_b200 import _capi
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(400, 4)).astype("f4")
+    y = (rng.uniform(size=400) < 0.5).astype("f4")
+    model = pm.LogisticGLM(X, y)
+    D, Cn = model.ndim, 8
+    s = np.array([0.3, 0.5, 0.2, 0.4, 0.25])
+    opts = dict(max_treedepth=6, early_max_treedepth=6, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75, t0=10.0,
+                adapt_step_size=1, adapt_mass=0, path_length=2.0, max_steps=64, hmc_jitter=0,
+                exec_mode=_capi.B2_EXEC_LOCKSTEP, glm_path=_capi.B2_GLM_SIMT)
+    q0 = rng.normal(size=(Cn, D)) * 0.1
+    seeds = np.arange(Cn, dtype=np.uint64) + 77
+    out = []
+    for dense in (False, True):
+        eng = model.engine(Cn, dtype="float64")
+        if dense:
+            eng.set_dense_mass(np.diag(s))
+            eng.set_state(q0, seeds, 0.2, np.zeros(D), np.ones(D), 0.0)
+        else:
+            eng.set_state(q0, seeds, 0.2, np.zeros(D), s ** 2, 0.0)
+        tr = eng.run(_capi.B2_NUTS, 12, 12, opts)
+        out.append({k: v.cpu().numpy() for k, v in tr.items()})
+        pos = eng.position()
+        assert np.allclose(pos, out[-1]["q"][-1], rtol=1e-12)              # position() speaks q as well
+        eng.close()
+    a, b = out
+    assert (a["tree_size"][:6] == b["tree_size"][:6]).all() and (a["depth"][:6] == b["depth"][:6]).all()
+    assert np.allclose(a["q"][:6], b["q"][:6], rtol=1e-7, atol=1e-9)
+    assert np.allclose(a["energy"][:6], b["energy"][:6], rtol=1e-9) and np.allclose(a["step_size"][:6], b["step_size"][:6], rtol=1e-9)
+    # a dense metric is static: asking the engine to adapt the diagonal next to it is refused
+    eng = model.engine(Cn, dtype="float64")
+    eng.set_dense_mass(np.diag(s))
+    eng.set_state(q0, seeds, 0.2, np.zeros(D), np.ones(D), 0.0)
+    with pytest.raises(_capi.B2Error, match="static"):
+        eng.run(_capi.B2_NUTS, 2, 2, dict(opts, adapt_mass=1))
+    eng.close()
+
+
+def test_dense_metric_on_a_correlated_posterior_through_the_tensor_core_likelihood():
+    """A GLM with correlated regressors in fp32 (tcgen05 likelihood under the reparameterisation): the dense metric built
+    from a pilot run's covariance gives the same posterior means as the adaptive diagonal run (|z| < 4 with the
+    chains' spread as scale) and needs shorter trees."""
+    rng = np.random.default_rng(8)
+    base = rng.normal(size=(20000, 1))
+    X = (0.9 * base + 0.45 * rng.normal(size=(20000, 6))).astype("f4")          # pairwise correlation ~0.8
+    beta = np.array([0.5, -0.3, 0.2, 0.1, -0.4, 0.3])
+    y = (rng.uniform(size=20000) < 1 / (1 + np.exp(-(0.2 + X @ beta)))).astype("f4")
+    with pm.LogisticGLM(X, y) as model:
+        pilot = pm.sample(300, tune=300, chains=128, step=pm.NUTS(), random_seed=5, compute_convergence_checks=False)
+    names = model.free_RVs
+    flat = np.concatenate([pilot[n].reshape(len(pilot[n]), -1) for n in names], axis=1)
+    cov = np.cov(flat, rowvar=0)
+    with model:
+        step = pm.NUTS(scaling=cov, is_cov=True)
+        assert step._batched and step._dense
+        dense = pm.sample(300, tune=300, chains=128, step=step, random_seed=6, compute_convergence_checks=False)
+    flat_d = np.concatenate([dense[n].reshape(len(dense[n]), -1) for n in names], axis=1)
+    sd = flat.std(axis=0)
+    z = (flat_d.mean(axis=0) - flat.mean(axis=0)) / (sd / np.sqrt(128 * 300 / 20.0))      # ESS >= draws / 20, conservatively
+    assert np.abs(z).max() < 4.0, z
+    assert np.allclose(flat_d.std(axis=0), sd, rtol=0.1)
+    t_diag = pilot.get_sampler_stats("tree_size")[-128 * 100:].mean()
+    t_dense = dense.get_sampler_stats("tree_size")[-128 * 100:].mean()
+    assert t_dense < 0.7 * t_diag, (t_dense, t_diag)
 
 
 def test_sample_callback_and_cancel():
