@@ -74,6 +74,7 @@ struct TcWorkspace {
     int n_tiles, c_pad, chain_tiles, splits, tiles_per_split, n_pad_rows;
     int first, count;        // the chains this workspace covers: [first, first + count)
     int post_levels;         // merge levels whose stack buffers the state-machine warps stage in shared memory
+    int x_policy;            // L2 hint of the X tile stream: 0 none, 1 evict_first (state and partials keep their lines), 2 evict_last
     int flush_tiles;         // the gradient accumulator is drained into the fp32 partials every flush_tiles tiles
     // Reference-centred positions.  Q enters GEMM1 as bf16 hi + lo, i.e. to ~17 bits RELATIVE TO |q|; near the
     // posterior mode that rounding of the position (2^-18 |q|) times the Hessian (N/4-ish) was the largest error of
@@ -498,12 +499,14 @@ k_glm_tc_main(TcWorkspace ws, TcWorkspace wsp, B2View<float> wview, double prior
         if (warp == 0) {
             // ===== producer: Q tile once, then the X tile ring =====
             if (lane == 0) {
+                const uint64_t x_pol = ws.x_policy == 2 ? l2_policy_evict_last() : l2_policy_evict_first();
                 for (int t = 0; t < T; ++t) {
                     const int s = t % STAGES;
                     if (t >= STAGES) mbar_wait(x_empty + s, ((t / STAGES) - 1) & 1, ws.err, 1);
                     const unsigned char* src = ws.xt + (size_t)(t_begin + t) * TC_STAGE_DATA;
                     mbar_expect_tx(x_full + s, TC_STAGE_DATA + TC_OBS * 4);
-                    bulk_g2s(x_s + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, x_full + s);
+                    if (ws.x_policy) bulk_g2s_hint(x_s + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, x_full + s, x_pol);
+                    else bulk_g2s(x_s + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, x_full + s);
                     bulk_g2s(y_s + s * TC_YS_BYTES, src + TC_STAGE_BYTES, TC_Y_BYTES, x_full + s);
                     bulk_g2s(y_s + s * TC_YS_BYTES + TC_Y_BYTES, ws.eta_ref + (size_t)(t_begin + t) * TC_OBS, TC_OBS * 4, x_full + s);
                 }
@@ -824,6 +827,10 @@ static int tc_setup(b2_engine* e, cudaStream_t stream) {
     // drains of the gradient accumulator: off by default here (<= 87 tiles = 1044 truncating adds per slab at C2,
     // a bias of ~3e-5 of a slab partial; each drain costs the pipeline 1-2 tile periods).  B2_TC_FLUSH=32 enables.
     shared.flush_tiles = env_int("B2_TC_FLUSH", 1 << 20);
+    // X tiles are streamed once per launch (52 MB at C2, more than a launch leaves of L2 anyway): marking their lines
+    // evict-first keeps the chains' state and the slab partials in L2 for the state-machine kernel (21.1 vs 22.4 us per
+    // step, likelihood +1 us: +1 % on the job, profiles/README.md).  B2_TC_XPOLICY=0 none, 2 evict_last.
+    shared.x_policy = env_int("B2_TC_XPOLICY", 1);
     if (shared.flush_tiles < 4) shared.flush_tiles = 4;
     B2_CUDA_OK(cudaMalloc(&shared.xt, (size_t)shared.n_tiles * TC_STAGE_DATA));
     B2_CUDA_OK(cudaMalloc(&shared.err, TC_ERR_INTS * sizeof(int)));
