@@ -573,13 +573,18 @@ def cpu_ess_run(wl, chains, tune, draws):
             "value": (g1 + g2) / wall, "unit": "grad-evals/s", "min_bulk_ess": ess, "min_bulk_ess_per_sec": ess / wall}
 
 
-def run_c2_small_ess(ctx, args):
-    """min-bulk-ESS/s of the GPU engine against the CPU arm ON THE SAME JOB: a reduced C2 (N = 20 000, D = 100,
-    200 tune + 200 draws) that the CPU port finishes in ~30 s on 8 cores; the GPU runs it with 1024 chains."""
+SMALL_ESS_JOBS = {"c2s": ("c2", dict(n_obs=20000, n_features=100)), "c3s": ("c3", dict(n_obs=20000))}
+
+
+def run_small_ess(ctx, args, name):
+    """min-bulk-ESS/s of the GPU engine against the CPU arm ON THE SAME JOB: a reduced C2 (N = 20 000, D = 100) or a
+    reduced C3 (N = 20 000 observations, 85 groups), 200 tune + 200 draws -- sizes the CPU port finishes in ~30 s on
+    8 cores; the GPU runs the same job with 1024 chains."""
     import argparse as _ap
+    base, shape = SMALL_ESS_JOBS[name]
     a2 = _ap.Namespace(**vars(args))
-    a2.n_obs, a2.n_features, a2.chains = 20000, 100, 0
-    wl = make_workload("c2", a2)
+    a2.n_obs, a2.n_features, a2.chains = shape.get("n_obs", 0), shape.get("n_features", 0), 0
+    wl = make_workload(base, a2)
     gpu = sample_config(ctx, a2, wl, 1024, 200, 200, split="strong")
     gpu.pop("_profile", None)
     strip_logs(gpu)
@@ -613,8 +618,8 @@ def run_b200(args):
             try:
                 if name == "c5":
                     res = run_c5(ctx, args, rows=args.c5_rows, tune_draws=(args.c5_iters // 2, args.c5_iters - args.c5_iters // 2))
-                elif name == "c2s":
-                    res = run_c2_small_ess(ctx, args)
+                elif name in SMALL_ESS_JOBS:
+                    res = run_small_ess(ctx, args, name)
                 else:
                     res = run_config(ctx, args, name)
             except Exception as err:                         # a failing side config must not take the headline down
@@ -766,7 +771,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c3", "c4", "c5"],
                     help="all = config 2 as the headline line + the other configs as shortened complete jobs under 'configs'")
-    ap.add_argument("--configs", default="c1,c3,c4,c5,c2s", help="side configs of --workload all (c2s = reduced C2 for the CPU ESS/s ratio)")
+    ap.add_argument("--configs", default="c1,c3,c4,c5,c2s,c3s",
+                    help="side configs of --workload all (c2s / c3s = reduced C2 / C3 for the CPU ESS/s ratio)")
     ap.add_argument("--c5-rows", type=int, default=6250000, help="rows per GPU of the side config c5")
     ap.add_argument("--c5-iters", type=int, default=30, help="transitions (tune + draws) of the side config c5")
     ap.add_argument("--skip-e2e", action="store_true")
