@@ -255,23 +255,40 @@ B2_HD bool b2_uturn(const G& g, int D, const T* var,
     // a lane's few components are summed in the vector dtype (only the signs of the totals matter), the
     // cross-lane reduction is fp64 like every other reduction
     T part[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
-    for (int i = g.lane(); i < D; i += G::NT) {
-        const T vr = var[i];
-        const T f1 = first1[i], l1 = last1[i], s1 = psum1[i];
-        const T f2 = first2[i], l2 = last2[i], s2 = psum2[i];
-        const T tot = s1 + s2;
-        part[0] += tot * (vr * f1);
-        part[1] += tot * (vr * l2);
-        if (extra) {
-            const T a = s1 + f2;
-            part[2] += a * (vr * f1);
-            part[3] += a * (vr * f2);
-            const T b = l1 + s2;
-            part[4] += b * (vr * l1);
-            part[5] += b * (vr * l2);
+    // Four components per pass, every load of the pass issued before the first store: the outputs alias the inputs
+    // (p_sum is updated in place), so a plain loop would serialise one memory round trip per component -- the
+    // operands of a block-per-chain group come from L2.
+    constexpr int UW = 4;
+    for (int i0 = g.lane(); i0 < D; i0 += UW * G::NT) {
+        T vr[UW], f1[UW], l1[UW], s1[UW], f2[UW], l2[UW], s2[UW];
+#pragma unroll
+        for (int u = 0; u < UW; ++u) {
+            const int i = i0 + u * G::NT;
+            const bool ok = i < D;
+            vr[u] = ok ? var[i] : (T)0;
+            f1[u] = ok ? first1[i] : (T)0; s1[u] = ok ? psum1[i] : (T)0;
+            l2[u] = ok ? last2[i] : (T)0; s2[u] = ok ? psum2[i] : (T)0;
+            l1[u] = (ok && extra) ? last1[i] : (T)0; f2[u] = (ok && extra) ? first2[i] : (T)0;
         }
-        if (out_psum) out_psum[i] = tot;
-        if (out_plast) out_plast[i] = l2;
+#pragma unroll
+        for (int u = 0; u < UW; ++u) {
+            const int i = i0 + u * G::NT;
+            const T tot = s1[u] + s2[u];
+            part[0] += tot * (vr[u] * f1[u]);
+            part[1] += tot * (vr[u] * l2[u]);
+            if (extra) {
+                const T a = s1[u] + f2[u];
+                part[2] += a * (vr[u] * f1[u]);
+                part[3] += a * (vr[u] * f2[u]);
+                const T b = l1[u] + s2[u];
+                part[4] += b * (vr[u] * l1[u]);
+                part[5] += b * (vr[u] * l2[u]);
+            }
+            if (i < D) {
+                if (out_psum) out_psum[i] = tot;
+                if (out_plast) out_plast[i] = l2[u];
+            }
+        }
     }
     double d[6] = {(double)part[0], (double)part[1], (double)part[2], (double)part[3], (double)part[4], (double)part[5]};
     g.allsum(d);
@@ -288,9 +305,19 @@ B2_HD void b2_copy(const G& g, int D, T* dst, const T* src) {
 // two copies with all loads in flight together (proposal position + gradient)
 template <typename T, typename G>
 B2_HD void b2_copy2(const G& g, int D, T* dst_a, const T* src_a, T* dst_b, const T* src_b) {
-    for (int i = g.lane(); i < D; i += G::NT) {
-        const T a = src_a[i], b = src_b[i];
-        dst_a[i] = a; dst_b[i] = b;
+    constexpr int UW = 4;                                  // all loads of a pass before its stores (see b2_uturn)
+    for (int i0 = g.lane(); i0 < D; i0 += UW * G::NT) {
+        T a[UW], b[UW];
+#pragma unroll
+        for (int u = 0; u < UW; ++u) {
+            const int i = i0 + u * G::NT;
+            a[u] = i < D ? src_a[i] : (T)0; b[u] = i < D ? src_b[i] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < UW; ++u) {
+            const int i = i0 + u * G::NT;
+            if (i < D) { dst_a[i] = a[u]; dst_b[i] = b[u]; }
+        }
     }
 }
 
