@@ -1,0 +1,8 @@
+run() { echo "== $*"; env "$@" timeout 300 python bench.py --workload c4 --skip-cpu --skip-e2e --no-clocks 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('value %.3f M grad-evals/s  device %.3f s  failed %s  min_ess %s  mean_tree %.1f' % (d['value']/1e6, d.get('job_seconds_device',0), d.get('failed_chains'), (d.get('ess') or {}).get('min_bulk_ess'), d.get('mean_tree_size',0)))"; }
+run A=1
+run A=2
+python profiles/sv_determinism.py 2>&1 | grep -v "acceptance\|tree depth" | tail -6
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -3

@@ -166,7 +166,8 @@ struct B2WarpGroup {                       // warp per chain
 template <int NTHREADS>
 struct B2BlockGroup {                      // block per chain (large D)
     static constexpr int NT = NTHREADS;
-    double* red;                           // shared scratch, >= 8 * (NT/32) doubles
+    double* red;                           // shared scratch, >= 2 * 8 * (NT/32) doubles: two halves used alternately
+    mutable int flip;                      // which half the next reduction writes (same in every thread)
     __device__ __forceinline__ int lane() const { return threadIdx.x; }
     template <int K> __device__ __forceinline__ void allsum(double (&x)[K]) const {
         static_assert(K <= 8, "scratch sized for 8 simultaneous sums");
@@ -177,23 +178,27 @@ struct B2BlockGroup {                      // block per chain (large D)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
         }
-        __syncthreads();                   // previous users of `red` are done
+        // One barrier per reduction: reduction n writes half n & 1.  A thread can only get to writing that half again
+        // (reduction n + 2) after the barrier of reduction n + 1, which every thread passes after it has read the
+        // results of reduction n.
+        double* buf = red + flip * (8 * NW);
+        flip ^= 1;
         if (l == 0) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) red[k * NW + w] = x[k];
+            for (int k = 0; k < K; ++k) buf[k * NW + w] = x[k];
         }
         __syncthreads();
         if (NW <= 8) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 double s = 0.0;
-                for (int j = 0; j < NW; ++j) s += red[k * NW + j];   // same order in every thread
+                for (int j = 0; j < NW; ++j) s += buf[k * NW + j];   // same order in every thread
                 x[k] = s;
             }
         } else {                           // 16 or 32 warps: one more butterfly, identical in every warp
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                double s = l < NW ? red[k * NW + l] : 0.0;
+                double s = l < NW ? buf[k * NW + l] : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 x[k] = s;

@@ -64,9 +64,9 @@ __global__ void k_logp_warp(B2ModelData m, const T* qA, const T* qB, T* gA, T* g
 template <typename T>
 __global__ void __launch_bounds__(B2_BLOCK_NT) k_logp_block(B2ModelData m, const T* qA, const T* qB, T* gA, T* gB,
                                                             int ld, const B2ChainState* st, int n, double* logp) {
-    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
+    __shared__ double red[2 * 8 * (B2_BLOCK_NT / 32)];
     B2BlockGroup<B2_BLOCK_NT> g;
-    g.red = red;
+    g.red = red; g.flip = 0;
     logp_group_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, m, qA, qB, gA, gB, ld, st, blockIdx.x, logp);
 }
 
@@ -87,9 +87,9 @@ __global__ void k_advance_warp(B2View<T> w, int resume_only) {
 
 template <typename T>
 __global__ void __launch_bounds__(B2_BLOCK_NT) k_advance_block(B2View<T> w, int resume_only) {
-    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
+    __shared__ double red[2 * 8 * (B2_BLOCK_NT / 32)];
     B2BlockGroup<B2_BLOCK_NT> g;
-    g.red = red;
+    g.red = red; g.flip = 0;
     const int c = blockIdx.x;
     B2ChainState s = w.st[c];
     if (resume_only) {
@@ -176,10 +176,10 @@ __global__ void k_persistent_warp(B2View<T> w, B2ModelData m, int hot_elems) {
 template <typename T, int NT, int CTAS>
 __global__ void __launch_bounds__(NT, CTAS) k_persistent_block(B2View<T> w, B2ModelData m, int hot_elems, int data_chip) {
     extern __shared__ __align__(16) unsigned char hot_raw[];
-    __shared__ double red[8 * (NT / 32)];
+    __shared__ double red[2 * 8 * (NT / 32)];
     __shared__ double lvh[4 * B2_MAX_LEVELS];
     B2BlockGroup<NT> g;
-    g.red = red;
+    g.red = red; g.flip = 0;
     persistent_body<T, B2BlockGroup<NT>>(g, w, m, blockIdx.x, hot_elems ? reinterpret_cast<T*>(hot_raw) : (T*)0, lvh,
                                          data_chip ? reinterpret_cast<T*>(hot_raw) + hot_elems : (T*)0);
 }
@@ -782,9 +782,9 @@ __global__ void k_lf_warp(B2View<T> w, int op, double eps, const T* q_in, const 
 template <typename T>
 __global__ void __launch_bounds__(B2_BLOCK_NT) k_lf_block(B2View<T> w, int op, double eps, const T* q_in, const T* p_in,
                                                           const double* var, T* q_out, T* p_out, double* energy) {
-    __shared__ double red[8 * (B2_BLOCK_NT / 32)];
+    __shared__ double red[2 * 8 * (B2_BLOCK_NT / 32)];
     B2BlockGroup<B2_BLOCK_NT> g;
-    g.red = red;
+    g.red = red; g.flip = 0;
     lf_body<T, B2BlockGroup<B2_BLOCK_NT>>(g, w, blockIdx.x, op, eps, q_in, p_in, var, q_out, p_out, energy);
 }
 
