@@ -774,7 +774,7 @@ def main():
     ap.add_argument("--configs", default="c1,c3,c4,c5,c2s,c3s",
                     help="side configs of --workload all (c2s / c3s = reduced C2 / C3 for the CPU ESS/s ratio)")
     ap.add_argument("--c5-rows", type=int, default=6250000, help="rows per GPU of the side config c5")
-    ap.add_argument("--c5-iters", type=int, default=60, help="transitions (tune + draws) of the side config c5")
+    ap.add_argument("--c5-iters", type=int, default=30, help="transitions (tune + draws) of the side config c5")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--iters-per-step", type=int, default=100)
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
