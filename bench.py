@@ -617,7 +617,11 @@ def run_b200(args):
             t0 = time.perf_counter()
             try:
                 if name == "c5":
-                    res = run_c5(ctx, args, rows=args.c5_rows, tune_draws=(args.c5_iters // 2, args.c5_iters - args.c5_iters // 2))
+                    # rows are weak-scaled, so the posterior narrows with the world size and the first transitions (far
+                    # start, step size not yet adapted) get long: at >= 4 ranks the side job is half as many transitions
+                    # (30 took 48 s at 8 ranks x 6.25 M rows); the per-leapfrog breakdown does not depend on the job length
+                    n5 = args.c5_iters if ctx.world <= 2 else max(12, args.c5_iters // 2)
+                    res = run_c5(ctx, args, rows=args.c5_rows, tune_draws=(n5 // 2, n5 - n5 // 2))
                 elif name in SMALL_ESS_JOBS:
                     res = run_small_ess(ctx, args, name)
                 else:
