@@ -623,7 +623,10 @@ def run_b200(args):
                     n5 = args.c5_iters if ctx.world <= 2 else max(12, args.c5_iters // 2)
                     res = run_c5(ctx, args, rows=args.c5_rows, tune_draws=(n5 // 2, n5 - n5 // 2))
                 elif name in SMALL_ESS_JOBS:
-                    res = run_small_ess(ctx, args, name)
+                    if ctx.world > 1:              # a CPU-ratio job: one GPU against the host cores, nothing to scale
+                        res = {"skipped": "GPU-vs-CPU ESS/s ratio on a reduced job: run at N = 1 only"}
+                    else:
+                        res = run_small_ess(ctx, args, name)
                 else:
                     res = run_config(ctx, args, name)
             except Exception as err:                         # a failing side config must not take the headline down
