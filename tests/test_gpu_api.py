@@ -313,6 +313,14 @@ def test_dense_mass_matrix_on_the_device():
         assert x.shape == (64 * 500, 3)
         assert np.abs(x.mean(axis=0) / sig).max() < 0.05 and np.allclose(x.std(axis=0), sig, rtol=0.03)
         assert 0.7 < trace.get_sampler_stats("mean_tree_accept").mean() < 0.95
+    with pm.StdNormal(3, sigma=sig):                      # HamiltonianMC through the same reparameterised seam
+        step = pm.HamiltonianMC(scaling=C, is_cov=True, dtype="float64")
+        assert step._batched and step._dense
+        trace = pm.sample(500, tune=300, chains=64, step=step, random_seed=12, compute_convergence_checks=False)
+    x = trace["x"]
+    assert np.abs(x.mean(axis=0) / sig).max() < 0.06 and np.allclose(x.std(axis=0), sig, rtol=0.04)
+    q1, stats = step.step({"x": np.zeros(3)})                # one chain, one draw: positions in and out are q, not z
+    assert np.isfinite(q1["x"]).all() and np.abs(q1["x"]).max() < 20 and "accept" in stats[0]
     from pymc3_b200.step_methods.hmc.quadpotential import QuadPotentialFullAdapt
     with pm.StdNormal(3, sigma=sig):
         with pytest.warns(UserWarning):
