@@ -16,7 +16,7 @@ from .backends import MultiTrace, NDArray, load_trace, merge_traces, save_trace 
 from .exceptions import ParallelSamplingError, SamplingError  # noqa: F401
 from .model import (EightSchoolsNCP, HierLinearNCP, LogisticGLM, Model, StdNormal, StochVol,  # noqa: F401
                     ValueGradFunction, modelcontext)
-from .sampling import init_nuts, iter_sample, sample  # noqa: F401
+from .sampling import init_nuts, iter_sample, sample, trace_cov  # noqa: F401
 from .stats import ess, rhat  # noqa: F401
 from .step_methods.hmc import NUTS, HamiltonianMC  # noqa: F401
 from .step_methods.hmc.quadpotential import (QuadPotentialDiag, QuadPotentialDiagAdapt,  # noqa: F401

@@ -23,7 +23,7 @@ from .exceptions import SamplingError
 from .model import modelcontext
 from .step_methods import step_sizes
 from .step_methods.hmc import NUTS
-from .step_methods.hmc.quadpotential import QuadPotentialDiagAdapt
+from .step_methods.hmc.quadpotential import QuadPotentialDiagAdapt, QuadPotentialFull
 
 _log = logging.getLogger("pymc3")
 
@@ -549,6 +549,17 @@ def iter_sample(draws, step, start=None, trace=None, chain=0, tune=None, model=N
     strace.close()
 
 
+def trace_cov(trace, vars=None, model=None):
+    """Covariance matrix of the flattened free variables over a trace (pymc3/tuning/scaling.py:113-141)."""
+    model = modelcontext(model)
+    names = list(model.free_RVs) if model is not None else list(vars if vars is not None else trace.varnames)
+    cols = []
+    for name in names:
+        x = np.asarray(trace[str(name)])
+        cols.append(x.reshape(x.shape[0], -1))
+    return np.cov(np.concatenate(cols, axis=1).T)
+
+
 def init_nuts(init="auto", chains=1, n_init=500000, model=None, random_seed=None, progressbar=True, **kwargs):
     """Starting points + an adaptive diagonal potential for NUTS (sampling.py:1837-2014).
 
@@ -574,9 +585,18 @@ def init_nuts(init="auto", chains=1, n_init=500000, model=None, random_seed=None
             for val in mean.values():
                 val[...] += 2 * np.random.rand(*val.shape) - 1
             start.append(mean)
-    elif init in ("advi+adapt_diag_grad", "advi+adapt_diag", "advi", "advi_map", "map", "nuts"):
+    elif init == "nuts":
+        # sampling.py:2002-2007: a pilot NUTS run; its covariance becomes a dense static metric (QuadPotentialFull, which
+        # the device runs in z = L^-1 q) and random pilot draws become the start points
+        with model:
+            pilot = sample(draws=n_init, step=NUTS(**kwargs), tune=n_init // 2, random_seed=random_seed,
+                           progressbar=progressbar, compute_convergence_checks=False)
+        cov = np.atleast_1d(trace_cov(pilot, model=model))
+        start = [pilot.point(int(i)) for i in np.random.randint(len(pilot), size=chains)]
+        return start, NUTS(potential=QuadPotentialFull(cov), model=model, **kwargs)
+    elif init in ("advi+adapt_diag_grad", "advi+adapt_diag", "advi", "advi_map", "map"):
         raise NotImplementedError("init=%r needs the variational / MAP subsystems, which are outside the "
-                                  "sampler hot path; use 'adapt_diag' or 'jitter+adapt_diag'" % init)
+                                  "sampler hot path; use 'adapt_diag', 'jitter+adapt_diag' or 'nuts'" % init)
     else:
         raise ValueError("Unknown initializer: {}.".format(init))
     mean = np.mean([model.dict_to_array(vals) for vals in start], axis=0)

@@ -333,3 +333,16 @@ def test_running_covariance_and_adaptive_dense_potential():
         for _ in range(300):
             g.update(np.random.randn(2), np.array([2.0, -0.5]), True)
         assert np.allclose(g._var, [0.25, 4.0], rtol=0.05)       # (the windows restart from one pseudo-gradient of 1)
+
+
+def test_trace_cov_matches_numpy():
+    """pymc3/tuning/scaling.py:113-141"""
+    rng = np.random.default_rng(0)
+    tr = {"a": rng.normal(size=(200, 2)), "b": rng.normal(size=200)}
+    tr["b"] = tr["b"] + tr["a"][:, 0]
+
+    class M:
+        free_RVs = ["a", "b"]
+    flat = np.column_stack([tr["a"], tr["b"]])
+    assert np.allclose(pm.trace_cov(tr, model=M()), np.cov(flat.T))
+

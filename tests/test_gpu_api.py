@@ -420,3 +420,24 @@ def test_sample_callback_and_cancel():
         trace = pm.sample(10, tune=0, chains=1, step=pm.NUTS(), random_seed=3, callback=cancel,
                           compute_convergence_checks=False)
     assert len(trace) == 5
+
+
+def test_init_nuts_pilot_run_gives_a_dense_metric():
+    """sampling.py:2002-2007: init='nuts' runs a pilot NUTS job, takes `trace_cov` of it as a static dense metric
+    (QuadPotentialFull, on the device) and pilot draws as start points."""
+    rng = np.random.default_rng(4)
+    base = rng.normal(size=(4000, 1))
+    X = (0.9 * base + 0.45 * rng.normal(size=(4000, 3))).astype("f4")
+    y = (rng.uniform(size=4000) < 1 / (1 + np.exp(-(X @ np.array([0.4, -0.2, 0.3]))))).astype("f4")
+    with pm.LogisticGLM(X, y) as model:
+        start, step = pm.init_nuts(init="nuts", chains=16, n_init=150, random_seed=3, progressbar=False)
+        assert type(step.potential).__name__ == "QuadPotentialFull" and step._batched and len(start) == 16
+        cov = step.potential._cov
+        assert cov.shape == (model.ndim, model.ndim) and np.all(np.linalg.eigvalsh(cov) > 0)
+        off = cov / np.sqrt(np.outer(np.diag(cov), np.diag(cov)))
+        assert np.abs(off - np.eye(model.ndim)).max() > 0.3            # the regressors are correlated: so is the posterior
+        trace = pm.sample(150, tune=100, chains=16, init="nuts", n_init=150, random_seed=5, progressbar=False,
+                          compute_convergence_checks=False)
+    assert np.allclose(pm.trace_cov(trace, model=model), cov, rtol=0.6, atol=0.3 * np.diag(cov).max())
+    assert 0.6 < trace.get_sampler_stats("mean_tree_accept").mean() < 0.97
+
