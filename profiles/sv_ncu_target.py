@@ -5,12 +5,13 @@ import time
 import numpy as np
 import torch
 sys.path.insert(0, ".")
+N_CHAINS = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 sys.argv = ["x"]
 import bench
 from pymc3_b200 import _capi
 import pymc3_b200 as pm
 
-C = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+C = N_CHAINS
 model = pm.StochVol()
 D = model.ndim
 opts = dict(max_treedepth=10, early_max_treedepth=8, Emax=1000.0, target_accept=0.8, gamma=0.05, k=0.75, t0=10.0,

@@ -569,11 +569,14 @@ static int run_t(b2_engine* e, const b2_sampler_opts* o, const b2_trace_out* tr,
         const size_t smem_sm = (size_t)227 * 1024;
         int ctas = 1, nt = e->D >= 2048 ? 512 : 256;
         if (blk) {
-            if (2 * (B2_V_EVERY_LEAPFROG * slot_bytes + 4096) <= smem_sm && 2 * (B2_V_STACK0 * slot_bytes + 4096) > smem_sm) { ctas = 2; nt = 256; }
+            // the lean layout (7 slots) pays when all 11 would not leave room for a second block; with no more chains
+            // than SMs a block has its SM to itself and takes 512 threads instead (+6 % at 64 / 148 chains)
+            const bool lean = 2 * (B2_V_EVERY_LEAPFROG * slot_bytes + 4096) <= smem_sm && 2 * (B2_V_STACK0 * slot_bytes + 4096) > smem_sm;
+            if (lean && e->C > e->sm_count) { ctas = 2; nt = 256; }
             ctas = env_choice("B2_PBLOCK_CTAS", ctas, 1, 2, 2);
             nt = env_choice("B2_PBLOCK_NT", nt, 256, 512, 1024);
             if (ctas == 2 && nt == 1024) nt = 512;
-            w.hot_slots = env_choice("B2_PBLOCK_HOT", ctas == 2 ? B2_V_EVERY_LEAPFROG : B2_V_STACK0, B2_V_EVERY_LEAPFROG, B2_V_STACK0, B2_V_STACK0);
+            w.hot_slots = env_choice("B2_PBLOCK_HOT", (lean || ctas == 2) ? B2_V_EVERY_LEAPFROG : B2_V_STACK0, B2_V_EVERY_LEAPFROG, B2_V_STACK0, B2_V_STACK0);
         }
         int hot_elems = w.hot_slots * e->Dp;
         size_t hot_bytes = (size_t)hot_elems * sizeof(T) * (blk ? 1 : B2_WARPS_PER_BLOCK);
