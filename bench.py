@@ -573,19 +573,20 @@ def cpu_ess_run(wl, chains, tune, draws):
             "value": (g1 + g2) / wall, "unit": "grad-evals/s", "min_bulk_ess": ess, "min_bulk_ess_per_sec": ess / wall}
 
 
-SMALL_ESS_JOBS = {"c2s": ("c2", dict(n_obs=20000, n_features=100)), "c3s": ("c3", dict(n_obs=20000))}
+SMALL_ESS_JOBS = {"c2s": ("c2", dict(n_obs=20000, n_features=100, chains=1024)),       # chains: the configs' own counts
+                  "c3s": ("c3", dict(n_obs=20000, chains=4096))}
 
 
 def run_small_ess(ctx, args, name):
     """min-bulk-ESS/s of the GPU engine against the CPU arm ON THE SAME JOB: a reduced C2 (N = 20 000, D = 100) or a
     reduced C3 (N = 20 000 observations, 85 groups), 200 tune + 200 draws -- sizes the CPU port finishes in ~30 s on
-    8 cores; the GPU runs the same job with 1024 chains."""
+    8 cores; the GPU runs the same job with the chain count of the full config (1024 / 4096)."""
     import argparse as _ap
     base, shape = SMALL_ESS_JOBS[name]
     a2 = _ap.Namespace(**vars(args))
     a2.n_obs, a2.n_features, a2.chains = shape.get("n_obs", 0), shape.get("n_features", 0), 0
     wl = make_workload(base, a2)
-    gpu = sample_config(ctx, a2, wl, 1024, 200, 200, split="strong")
+    gpu = sample_config(ctx, a2, wl, shape["chains"], 200, 200, split="strong")
     gpu.pop("_profile", None)
     strip_logs(gpu)
     out = {"workload": wl["label"], "gpu": {k: gpu[k] for k in ("value", "chains_total", "tune", "draws", "job_seconds_wall",
