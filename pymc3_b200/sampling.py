@@ -84,6 +84,11 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
     if draws < 1:
         raise ValueError("Argument `draws` must be greater than 0.")
 
+    if isinstance(step, (list, tuple)):                   # sampling.py:142-165 builds a CompoundStep from a list
+        if len(step) != 1:
+            raise NotImplementedError("CompoundStep (several step methods on disjoint variables, step_methods/compound.py) "
+                                      "is outside the device path: the engine samples all continuous variables jointly")
+        step = step[0]
     if step is None:
         _log.info("Auto-assigning NUTS sampler...")
         start_, step = init_nuts(init=init, chains=chains, n_init=n_init, model=model,

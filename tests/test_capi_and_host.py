@@ -335,6 +335,15 @@ def test_running_covariance_and_adaptive_dense_potential():
         assert np.allclose(g._var, [0.25, 4.0], rtol=0.05)       # (the windows restart from one pseudo-gradient of 1)
 
 
+def test_step_lists_are_unwrapped_or_refused():
+    """sampling.py:142-165: a list of step methods becomes a CompoundStep; one HMC-family step is just that step"""
+    with pm.StdNormal(2):
+        with pytest.raises(NotImplementedError, match="CompoundStep"):
+            pm.sample(5, tune=0, chains=1, step=[object(), object()])
+        with pytest.raises(NotImplementedError, match="NUTS / HamiltonianMC"):
+            pm.sample(5, tune=0, chains=1, step=[object()])
+
+
 def test_trace_cov_matches_numpy():
     """pymc3/tuning/scaling.py:113-141"""
     rng = np.random.default_rng(0)
