@@ -113,7 +113,7 @@ def sample(draws=500, step=None, init="auto", n_init=200000, start=None, trace=N
     t_start = time.time()
     if getattr(step, "_batched", False):
         mtrace = _sample_batched(step, model, draws, tune, chains, start, random_seed, devices, chain_idx,
-                                 callback=callback, chunk=chunk, run_ahead=run_ahead)
+                                 callback=callback, chunk=chunk, run_ahead=run_ahead, progressbar=progressbar)
     else:
         # a user potential / step_rand: chains one after the other, draws one at a time through step.step(),
         # like the reference's _sample_many -> _iter_sample (sampling.py:786-936)
@@ -331,8 +331,21 @@ def _np_dtype(t):
             torch.int64: np.int64}[t.dtype]
 
 
+def _progress(total, chains, enabled):
+    """the reference's progress bar (sampling.py:1370-1382, fastprogress there), advanced once per chunk; only on a
+    terminal, so logs and pipes stay clean"""
+    import sys
+    if not enabled or not sys.stderr.isatty():
+        return None
+    try:
+        from tqdm import tqdm
+    except ImportError:
+        return None
+    return tqdm(total=total, unit="draw", desc="Sampling %d chains" % chains, leave=False, mininterval=0.5)
+
+
 def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, chain_idx=0, callback=None,
-                    chunk=None, run_ahead=True):
+                    chunk=None, run_ahead=True, progressbar=False):
     """All chains in one engine per device; chains are split contiguously over devices.
 
     The job runs in chunks of `chunk` transitions (default 100; 1 when a `callback` is given, so that it sees
@@ -380,6 +393,7 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
     n_chunks = (draws + chunk - 1) // chunk
     prof_from = n_chunks - int(getattr(step, "_profile_last_chunks", 0) or 0)
     prof = None
+    bar = _progress(draws, chains, progressbar)
     try:
         while done < draws:
             n = min(chunk, draws - done)
@@ -389,12 +403,17 @@ def _sample_batched(step, model, draws, tune, chains, start, seeds, devices, cha
                 prof = {"n_grad0": sum(rep.n_grad for r in runs for rep in r.eng.reports()), "t0": time.perf_counter()}
             run_all(n)
             done += n
+            if bar is not None:
+                bar.update(n)
             if callback is not None:
                 for r in runs:
                     r.flush()
                 _chunk_callbacks(callback, step, model, runs, shards, done - n, done, draws, tune, chain_idx, stat_dtypes)
     except KeyboardInterrupt:
         interrupted = True
+    finally:
+        if bar is not None:
+            bar.close()
 
     if prof is not None:
         like = [r.eng.profile() for r in runs]
